@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|bm25|fuse]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic queries.  At N=1 the default
+workload is BASELINE.json configs[1] (dense flat-IP top-100, 10M x 1024 bf16, 4096 queries).  With N
+ranks every rank owns its own 10M-row shard (the corpus grows to N x 10M: weak scaling), computes its
+local top-k and the lists are merged after one NCCL all-gather.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hybrid queries/sec @k=100 (1/2/4/8 B200); dense/MaxSim scan GB/s vs HBM peak"
+UNIT = "queries/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "bf16_tflops_burst": p["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# =================================================================================================
+# workloads
+# =================================================================================================
+class DenseWorkload:
+    """BASELINE.json configs[1]: dense flat inner-product top-100, 10M x 1024 bf16 per GPU, 4096 queries."""
+    name = "dense_flat_ip_top100"
+    dtype = "bf16"
+
+    def __init__(self, args, rank, world, device):
+        self.N, self.d, self.nq, self.k = args.n_docs or 10_000_000, args.dim or 1024, args.nq or 4096, args.k
+        self.rank, self.world, self.device = rank, world, device
+
+    def config(self):
+        return {"workload": f"configs[1] dense flat-IP top-{self.k}: {self.N} x {self.d} bf16 rows per GPU, batch {self.nq} queries",
+                "n_docs_per_gpu": self.N, "dim": self.d, "batch_queries": self.nq, "k": self.k,
+                "corpus_rows_total": self.N * self.world,
+                "parallelism": f"doc-sharded x{self.world}, local top-k + NCCL all-gather + k-way merge" if self.world > 1 else "single GPU",
+                "l2": f"corpus shard {self.N * self.d * 2 / 1e9:.2f} GB >> 126 MB L2 (no flush needed)",
+                "value_definition": "rank-level query scans per second: every rank answers the whole batch against its own shard, "
+                                    "value = n_gpus * batch_queries * steps / time (queries/s normalised to one shard's corpus)"}
+
+    def setup(self):
+        import torch
+        from legal_rag_b200 import engine, synth
+        self.torch, self.engine = torch, engine
+        self.X = synth.unit_rows_bf16(self.N, self.d, 2 + self.rank, self.device)
+        self.Q = synth.unit_rows_bf16(self.nq, self.d, 3, self.device, chunk=self.nq)
+        self.shard = engine.FlatIPShard(self.X, id_base=self.rank * self.N)
+        self.Q_host = self.Q.cpu().pin_memory()
+        self.launches_per_step = 3 + (1 if self.world > 1 else 0)
+
+    def step(self):
+        return self.shard.search_device(self.Q, self.k)
+
+    def e2e_step(self):
+        return self.shard.search(self.Q_host, self.k)
+
+    def e2e_bytes(self):
+        return self.nq * self.d * 2, self.nq * self.k * 12
+
+    def units_per_step(self):
+        return self.nq * self.world
+
+    dominant = "dense_scan"
+
+    def roofline(self, kernel_ms, peaks):
+        flops = 2.0 * self.nq * self.N * self.d
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "traffic": None, "kernel": "dense_scan_kernel", "kernel_ms": kernel_ms,
+                "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per launch", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                "scan_gbs": self.N * self.d * 2 / (kernel_ms * 1e-3) / 1e9}
+
+    # ---- CPU leg: oracle flat-IP (numpy fp32 BLAS + exact top-k) on a bounded sample ----
+    def cpu_sample(self, budget_s=15.0):
+        import numpy as np
+        from oracle import dense as odense
+        n_s, nq_s = 200_000, 256
+        rng = np.random.default_rng(2)
+        X = rng.standard_normal((n_s, self.d), dtype=np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q = rng.standard_normal((nq_s, self.d), dtype=np.float32)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+
+        def run():
+            t0 = time.perf_counter()
+            odense.flat_ip_topk(Q, X, self.k)
+            dt = time.perf_counter() - t0
+            # linear in corpus rows: time for the full shard = dt * N / n_s
+            return nq_s / (dt * self.N / n_s), dt
+        sample = (f"oracle numpy-fp32 flat-IP + exact top-{self.k}: {nq_s} queries x {n_s} of the {self.N} rows per step, "
+                  f"extrapolated linearly in rows to the full shard")
+        return run, sample
+
+
+class MaxsimWorkload:
+    """BASELINE.json configs[2]: ColBERT MaxSim rerank, docs x 128 tokens x 128-d, 32-token queries, 1000 -> 100."""
+    name = "maxsim_rerank"
+    dtype = "bf16"
+    dominant = "maxsim"
+
+    def __init__(self, args, rank, world, device):
+        self.Nd, self.Ld, self.Lq = args.n_docs or 1_000_000, 128, 32
+        self.nq, self.C, self.k = args.nq or 1024, 1000, args.k
+        self.rank, self.world, self.device = rank, world, device
+
+    def config(self):
+        return {"workload": f"configs[2] MaxSim rerank: {self.Nd} docs x {self.Ld} x 128 bf16, {self.nq} queries x {self.Lq} tokens, "
+                            f"{self.C} candidates -> top-{self.k}", "l2": "gathered bytes per step 33.5 GB >> L2",
+                "parallelism": f"x{self.world} replicas of the token store" if self.world > 1 else "single GPU"}
+
+    def setup(self):
+        import torch
+        from legal_rag_b200 import engine, synth
+        self.torch, self.engine = torch, engine
+        self.D = synth.unit_tokens_bf16(self.Nd, self.Ld, 128, 5, self.device)
+        self.Q = synth.unit_tokens_bf16(self.nq, self.Lq, 128, 7, self.device)
+        g = torch.Generator(device=self.device); g.manual_seed(8)
+        self.cand = torch.stack([torch.randperm(self.Nd, generator=g, device=self.device)[:self.C] for _ in range(self.nq)]) \
+            if self.Nd * self.nq <= 2 ** 26 else torch.randint(0, self.Nd, (self.nq, self.C), generator=g, device=self.device)
+        self.Q_host = self.Q.cpu().pin_memory()
+        self.cand_host = self.cand.cpu().pin_memory()
+        self.launches_per_step = 2
+
+    def step(self):
+        return self.engine.maxsim_rerank(self.D, None, self.Q, self.cand, self.k)
+
+    def e2e_step(self):
+        q = self.Q_host.to(self.device, non_blocking=True)
+        c = self.cand_host.to(self.device, non_blocking=True)
+        s, i = self.engine.maxsim_rerank(self.D, None, q, c, self.k)
+        return s.cpu(), i.cpu()
+
+    def e2e_bytes(self):
+        return self.nq * self.Lq * 128 * 2 + self.nq * self.C * 8, self.nq * self.k * 12
+
+    def units_per_step(self):
+        return self.nq * self.world
+
+    def roofline(self, kernel_ms, peaks):
+        nbytes = float(self.nq) * self.C * self.Ld * 128 * 2
+        ach = nbytes / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "kernel": "maxsim_kernel", "kernel_ms": kernel_ms, "algorithmic": f"nq*C*Ld*dim*2 = {nbytes:.3e} B per launch",
+                "peak_source": peaks["source"] + " (copy bandwidth)"}
+
+    def cpu_sample(self, budget_s=15.0):
+        import numpy as np
+        from oracle import maxsim as omaxsim
+        n_s, nq_s = 4000, 8
+        rng = np.random.default_rng(5)
+        D = rng.standard_normal((n_s, self.Ld, 128), dtype=np.float32)
+        Q = rng.standard_normal((nq_s, self.Lq, 128), dtype=np.float32)
+        cand = np.stack([rng.permutation(n_s)[:self.C] for _ in range(nq_s)])
+
+        def run():
+            t0 = time.perf_counter()
+            omaxsim.rerank_topk(Q, D, None, cand, self.k)
+            dt = time.perf_counter() - t0
+            return nq_s / dt, dt
+        return run, f"oracle numpy-fp32 MaxSim: {nq_s} queries x {self.C} candidates x {self.Ld} tokens per step (full per-query work)"
+
+
+WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload}
+
+
+# =================================================================================================
+def run_reference(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port; the third-party wheels it calls are not
+    installable here) on the host cores."""
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload](args, 0, 1, None)
+    run, sample = wl.cpu_sample()
+    for _ in range(max(1, min(args.warmup, 2))):
+        run()
+    vals, t = [], 0.0
+    for _ in range(args.steps):
+        v, dt = run()
+        vals.append(v); t += dt
+    value = len(vals) / sum(1.0 / v for v in vals)   # harmonic mean == total queries / total time
+    cores = os.cpu_count()
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-docs", type=int, default=0)
+    ap.add_argument("--dim", type=int, default=0)
+    ap.add_argument("--nq", type=int, default=0)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback (use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from legal_rag_b200 import engine
+
+    wl = WORKLOADS[args.workload](args, rank, world, device)
+    wl.setup()
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        wl.step()
+    barrier()
+    engine.prof_enable(args.steps * 4 + 8)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = wl.step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    prof = engine.prof_collect()
+    engine.prof_enable(0)
+    kern = [t for name, t in prof if name == wl.dominant]
+    kernel_ms = sum(kern) / max(1, len(kern))
+
+    # ---- end to end through the host-buffer API: H2D queries -> search -> D2H results, every step ----
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        wl.e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = t.tolist()
+
+    if rank == 0:
+        units = wl.units_per_step() * args.steps
+        value = units / (ms * 1e-3)
+        h2d, d2h = wl.e2e_bytes()
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+                "data": "synthetic (seeded, generated on device; random unit-norm vectors)", "config": wl.config(),
+                "clocks": clocks,
+                "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": wl.launches_per_step * args.steps,
+                "roofline": wl.roofline(kernel_ms, peaks),
+                "global_queries_per_s": wl.nq * args.steps / (ms * 1e-3)}
+        if not args.no_cpu_baseline:
+            run, sample = wl.cpu_sample()
+            run()
+            vals, t0 = [], time.perf_counter()
+            while time.perf_counter() - t0 < 12.0 and len(vals) < 20:
+                vals.append(run()[0])
+            v = len(vals) / sum(1.0 / x for x in vals)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+/* liblrag -- C ABI of the B200-native hybrid-retrieval engine (sm_100a only).
+ *
+ * The reference (Fan-Luo/Legal-RAG) is pure Python and has no FFI of its own: its hot
+ * path bottoms out in three third-party objects.  Each entry point below replaces one
+ * of those call sites (cited per function; paths are relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C symbols, no torch / C++ types in any signature;
+ *   - every tensor argument is a DEVICE pointer (torch.Tensor.data_ptr()); row-major;
+ *   - work is enqueued on the caller's stream and the call returns without
+ *     synchronising;
+ *   - no allocation inside: the caller passes a workspace of at least
+ *     <fn>_workspace_bytes(...) bytes, 256-byte aligned;
+ *   - return 0 on success, a negative LRAG_E* code otherwise; lrag_last_error() gives
+ *     the thread-local message;
+ *   - no global mutable state after lrag_init: callable concurrently from any host
+ *     thread on distinct streams with distinct workspaces;
+ *   - no CPU fallback: lrag_init fails on anything that is not compute capability 10.x.
+ *
+ * Result ordering everywhere: (score descending, id ascending); rows shorter than k are
+ * padded with (LRAG_PAD_SCORE, -1).
+ */
+#ifndef LRAG_H_
+#define LRAG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRAG_VERSION 100
+
+#define LRAG_OK 0
+#define LRAG_EINVAL (-1)   /* bad argument                                   */
+#define LRAG_ENOSPC (-2)   /* workspace too small                            */
+#define LRAG_ECUDA (-3)    /* CUDA runtime / driver error                    */
+#define LRAG_EARCH (-4)    /* device is not sm_100 (no fallback path exists) */
+
+#define LRAG_PAD_SCORE (-3.4028234663852886e38f) /* faiss pads with lowest float */
+#define LRAG_MAX_K 1024
+#define LRAG_BM25_MAX_QUERY_TERMS 128 /* tokens per query, repeats included */
+
+/* opaque stream handle: a cudaStream_t (torch.cuda.current_stream().cuda_stream) */
+typedef void* lrag_stream_t;
+
+int lrag_version(void);
+/* Binds to `device`, checks the architecture, caches SM count and the driver's
+ * tensor-map encoder.  Must be called once per device before any other call. */
+int lrag_init(int device);
+const char* lrag_last_error(void);
+/* number of SMs the persistent kernels size their grids with (148 on B200) */
+int lrag_sm_count(void);
+
+/* Launch profiler (bench.py's roofline leg): after lrag_prof_enable(capacity) every launch of a
+ * dominant kernel is bracketed by a CUDA event pair on the launching stream.  lrag_prof_collect
+ * synchronises on them, writes up to max_n durations (ms) and kernel tags (0 dense scan, 1 BM25
+ * scan, 2 MaxSim, 3 fusion) and returns how many it wrote (negative = error); the ring restarts.
+ * lrag_prof_enable(0) switches it off.  Single-threaded use only. */
+int lrag_prof_enable(int capacity);
+int lrag_prof_collect(float* ms, int* tag, int max_n);
+
+/* ---------------------------------------------------------------------------------
+ * Dense channel.  Replaces faiss `index.search(q_vec, k)` at
+ * legalrag/retrieval/dense_retriever.py:42 and legalrag/retrieval/vector_store.py:169
+ * (IndexFlat, METRIC_INNER_PRODUCT): D, I = topk_k(Q . X^T).
+ *   X [N, d] bf16, Q [nq, d] bf16, d % 8 == 0 (16-byte rows for TMA), 1 <= k <= LRAG_MAX_K.
+ *   out_id = id_base + row index in X  (id_base: first global doc id of this shard).
+ * One fused pass: tcgen05 bf16 contraction with TMA-staged corpus tiles, per-query
+ * running-threshold candidate filter in the TMEM epilogue, then an exact select.
+ * The [nq, N] score matrix is never written. */
+size_t lrag_dense_topk_workspace_bytes(int64_t N, int d, int nq, int k);
+int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void* Q, int nq, int k,
+                         int64_t id_base, float* out_score, int64_t* out_id, void* ws,
+                         size_t ws_bytes, lrag_stream_t stream);
+/* CUDA-core cross-check of the same contract (fp32 FMA, materialises [nq, N] scores in
+ * the workspace).  Test instrument for the tcgen05 path; small shapes only. */
+size_t lrag_dense_topk_ref_workspace_bytes(int64_t N, int d, int nq, int k);
+int lrag_dense_topk_bf16_ref(const void* X, int64_t N, int d, const void* Q, int nq, int k,
+                             int64_t id_base, float* out_score, int64_t* out_id, void* ws,
+                             size_t ws_bytes, lrag_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * Exact row-wise top-k of a materialised fp32 score matrix S [nq, ld] (first N columns
+ * of each row are live).  Replaces the `sorted(range(N), key=scores[i], reverse=True)[:k]`
+ * of legalrag/retrieval/bm25_retriever.py:75 for small corpora and ranks MaxSim
+ * candidate scores.  If `col_id` is non-NULL ([nq, N] int64) the returned id is
+ * col_id[row, col] (entries with col_id < 0 are skipped); else id_base + col. */
+size_t lrag_topk_select_workspace_bytes(int nq, int64_t N, int k);
+int lrag_topk_select_f32(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base,
+                         const int64_t* col_id, float* out_score, int64_t* out_id, void* ws,
+                         size_t ws_bytes, lrag_stream_t stream);
+
+/* k-way merge of per-shard candidate lists (the step after the NCCL all-gather; no
+ * reference counterpart -- the reference is single-process).  score/id [nq, L];
+ * id < 0 entries are padding. */
+int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
+                    float* out_score, int64_t* out_id, lrag_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * BM25 channel.  Replaces `bm25.get_scores(tokens)` + the full Python sort at
+ * legalrag/retrieval/bm25_retriever.py:74-75 (rank_bm25.BM25Okapi).
+ * Index = term-major CSR with doc ids ascending inside each term:
+ *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard), impact [nnz] fp32
+ *   = idf[t] * tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))  with GLOBAL idf/avgdl.
+ * Queries = CSR of term ids: q_indptr [nq+1] int64, q_term [*] int32 (repeats allowed and
+ * scored once per occurrence, -1 / out-of-range = OOV).
+ * Every document is a candidate: documents matching no term score 0 and are returned,
+ * lowest id first, when fewer than k documents match (the reference's behaviour).
+ * `max_query_terms` = the longest query's token count (host-side knowledge of q_indptr; at most
+ * LRAG_BM25_MAX_QUERY_TERMS).  `nonneg` != 0 asserts every impact >= 0 (true whenever the corpus'
+ * average idf is positive): doc slabs no query term touches are then skipped and zero-score
+ * documents are filled in by id; with nonneg == 0 every document of every slab is ranked. */
+size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
+int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,
+                   const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                   int64_t N, int k, int64_t id_base, int nonneg, float* out_score, int64_t* out_id,
+                   void* ws, size_t ws_bytes, lrag_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * ColBERT channel.  Replaces the scoring inside `Searcher.search(query, k)` at
+ * legalrag/retrieval/colbert_retriever.py:152 (colbert_score: sum_i max_j <q_i, d_j>).
+ *   D [Nd, Ld, dim] bf16 token store (dim == 128, Ld <= 256, Ld % 8 == 0), doclen [Nd]
+ *   int32 or NULL (= Ld), Q [nq, Lq, dim] bf16 (Lq <= 32), cand [nq, C] int64 LOCAL rows
+ *   (-1 = skip).  out_id = id_base + row.  Fused: per candidate one tcgen05 tile
+ *   (doc tokens x query tokens) whose row-max / sum epilogue runs out of TMEM; the
+ *   [Lq, Ld] similarity matrix is never written. */
+size_t lrag_maxsim_rerank_workspace_bytes(int nq, int C, int k);
+int lrag_maxsim_rerank_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim,
+                            const void* Q, int nq, int Lq, const int64_t* cand, int C, int k,
+                            int64_t id_base, float* out_score, int64_t* out_id, void* ws,
+                            size_t ws_bytes, lrag_stream_t stream);
+/* candidate scores only, [nq, C] fp32 (-inf for skipped) -- the multi-GPU path scores the
+ * candidates each shard owns and combines them with a max-reduce. */
+int lrag_maxsim_scores_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim,
+                            const void* Q, int nq, int Lq, const int64_t* cand, int C,
+                            float* out_score, lrag_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * Fusion.  Replaces HybridRetriever._fuse (legalrag/retrieval/hybrid_retriever.py:389-551,
+ * _minmax :24-30, _rrf_with_breakdown :33-56) plus the min_final_score filter (:309-310)
+ * and the final slice (:384).  Inputs are the three per-channel lists, each [nq, kc],
+ * already sorted (score desc), id == -1 = padding; a NULL channel is empty.
+ * method: 0 weighted_sum, 1 rrf, 2 wrrf, 3 rrf_norm_blend.
+ * out_breakdown (optional, [nq, k, 8] fp32): rrf_norm, weighted_sum, dense_norm,
+ * bm25_norm, colbert_norm, contrib_dense, contrib_bm25, contrib_colbert. */
+int lrag_fuse_topk(const float* s_dense, const int64_t* i_dense, const float* s_bm25,
+                   const int64_t* i_bm25, const float* s_colb, const int64_t* i_colb, int nq,
+                   int kc, int k, int method, double w_dense, double w_bm25, double w_colb,
+                   int rrf_k, double alpha, double min_final, float* out_score, int64_t* out_id,
+                   float* out_breakdown, lrag_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRAG_H_ */

@@ -1,0 +1,311 @@
+"""Batched tensor API over liblrag: what sits between the reference-shaped retriever classes and
+the C ABI.  Every function takes CUDA tensors, enqueues on the current torch stream and returns
+(scores float32 [nq, k], ids int64 [nq, k]) ordered (score desc, id asc), padded with
+(PAD_SCORE, -1).  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+from ._native import LRAG_BM25_MAX_QUERY_TERMS, LRAG_MAX_K, PAD_SCORE, LragError, check
+
+FUSION_METHODS = {"weighted_sum": 0, "rrf": 1, "wrrf": 2, "rrf_norm_blend": 3}
+BREAKDOWN_FIELDS = ("rrf_norm", "weighted_sum", "dense_norm", "bm25_norm", "colbert_norm",
+                    "contrib_dense", "contrib_bm25", "contrib_colbert")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _need(t: torch.Tensor, dtype, ndim: int, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise LragError(f"{name} must be a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype or t.dim() != ndim:
+        raise LragError(f"{name}: expected {ndim}-d {dtype}, got {t.dim()}-d {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _out(nq: int, k: int, device):
+    return (torch.empty((nq, k), dtype=torch.float32, device=device),
+            torch.empty((nq, k), dtype=torch.int64, device=device))
+
+
+# ------------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------------
+def dense_topk(X: torch.Tensor, Q: torch.Tensor, k: int, id_base: int = 0, *, reference_kernel: bool = False
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Exact flat inner-product top-k: X [N, d] bf16 corpus shard, Q [nq, d] bf16 queries.
+
+    reference_kernel=True runs the CUDA-core cross-check kernel instead of the tcgen05 scan
+    (tests only; it materialises the [nq, N] score matrix)."""
+    lib = _native.init(X.device.index)
+    X = _need(X, torch.bfloat16, 2, "X")
+    Q = _need(Q, torch.bfloat16, 2, "Q")
+    N, d = X.shape
+    nq = Q.shape[0]
+    if Q.shape[1] != d:
+        raise LragError(f"Q has d={Q.shape[1]}, corpus has d={d}")
+    s, i = _out(nq, k, X.device)
+    if reference_kernel:
+        ws = _ws(lib.lrag_dense_topk_ref_workspace_bytes(N, d, nq, k), X.device)
+        rc = lib.lrag_dense_topk_bf16_ref(_ptr(X), N, d, _ptr(Q), nq, k, id_base, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+    else:
+        ws = _ws(lib.lrag_dense_topk_workspace_bytes(N, d, nq, k), X.device)
+        rc = lib.lrag_dense_topk_bf16(_ptr(X), N, d, _ptr(Q), nq, k, id_base, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+    check(rc, "lrag_dense_topk_bf16")
+    return s, i
+
+
+def dense_workspace_bytes(N: int, d: int, nq: int, k: int) -> int:
+    return int(_native.load().lrag_dense_topk_workspace_bytes(N, d, nq, k))
+
+
+# ------------------------------------------------------------------------------------------------
+# generic select / merge
+# ------------------------------------------------------------------------------------------------
+def topk_select(S: torch.Tensor, k: int, id_base: int = 0, col_id: Optional[torch.Tensor] = None):
+    lib = _native.init(S.device.index)
+    S = _need(S, torch.float32, 2, "S")
+    nq, N = S.shape
+    if col_id is not None:
+        col_id = _need(col_id, torch.int64, 2, "col_id")
+    s, i = _out(nq, k, S.device)
+    check(lib.lrag_topk_select_f32(_ptr(S), N, nq, N, k, id_base, _ptr(col_id), _ptr(s), _ptr(i), None, 0, _stream()),
+          "lrag_topk_select_f32")
+    return s, i
+
+
+def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k: int):
+    """k-way merge of concatenated per-shard lists [nq, L] (id < 0 = padding)."""
+    lib = _native.init(scores.device.index)
+    scores = _need(scores, torch.float32, 2, "scores")
+    ids = _need(ids, torch.int64, 2, "ids")
+    nq, L = scores.shape
+    s, i = _out(nq, k, scores.device)
+    check(lib.lrag_topk_merge(_ptr(scores), _ptr(ids), nq, L, k, _ptr(s), _ptr(i), _stream()), "lrag_topk_merge")
+    return s, i
+
+
+# ------------------------------------------------------------------------------------------------
+# BM25
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class Bm25DeviceIndex:
+    """Term-major CSR postings of one shard, resident in HBM.
+
+    impact[p] = idf[t] * tf * (k1 + 1) / (tf + k1 * (1 - b + b * dl / avgdl)) with GLOBAL idf / avgdl,
+    doc_id local to the shard and ascending inside each term."""
+    indptr: torch.Tensor      # [V + 1] int64
+    doc_id: torch.Tensor      # [nnz] int32
+    impact: torch.Tensor      # [nnz] float32
+    n_docs: int
+    nonneg: bool
+    id_base: int = 0
+
+    @property
+    def vocab(self) -> int:
+        return int(self.indptr.numel() - 1)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.doc_id.numel())
+
+
+def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int, k: int):
+    """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV)."""
+    lib = _native.init(index.indptr.device.index)
+    dev = index.indptr.device
+    q_indptr = _need(q_indptr, torch.int64, 1, "q_indptr")
+    q_term = _need(q_term, torch.int32, 1, "q_term")
+    nq = q_indptr.numel() - 1
+    if max_query_terms > LRAG_BM25_MAX_QUERY_TERMS:
+        raise LragError(f"a query has {max_query_terms} tokens; at most {LRAG_BM25_MAX_QUERY_TERMS} are supported")
+    s, i = _out(nq, k, dev)
+    ws = _ws(lib.lrag_bm25_topk_workspace_bytes(index.n_docs, nq, k, max_query_terms), dev)
+    rc = lib.lrag_bm25_topk(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, _ptr(q_indptr),
+                            _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
+                            _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+    check(rc, "lrag_bm25_topk")
+    return s, i
+
+
+# ------------------------------------------------------------------------------------------------
+# ColBERT MaxSim
+# ------------------------------------------------------------------------------------------------
+def maxsim_scores(D: torch.Tensor, doclen: Optional[torch.Tensor], Q: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
+    """D [Nd, Ld, 128] bf16, doclen [Nd] int32 or None, Q [nq, Lq, 128] bf16, cand [nq, C] int64 local rows
+    (-1 = skip) -> [nq, C] float32 (-inf for skipped)."""
+    lib = _native.init(D.device.index)
+    D = _need(D, torch.bfloat16, 3, "D")
+    Q = _need(Q, torch.bfloat16, 3, "Q")
+    cand = _need(cand, torch.int64, 2, "cand")
+    if doclen is not None:
+        doclen = _need(doclen, torch.int32, 1, "doclen")
+    Nd, Ld, dim = D.shape
+    nq, Lq, _ = Q.shape
+    C = cand.shape[1]
+    out = torch.empty((nq, C), dtype=torch.float32, device=D.device)
+    check(lib.lrag_maxsim_scores_bf16(_ptr(D), _ptr(doclen), Nd, Ld, dim, _ptr(Q), nq, Lq, _ptr(cand), C, _ptr(out), _stream()),
+          "lrag_maxsim_scores_bf16")
+    return out
+
+
+def maxsim_rerank(D, doclen, Q, cand, k: int, id_base: int = 0):
+    lib = _native.init(D.device.index)
+    D = _need(D, torch.bfloat16, 3, "D")
+    Q = _need(Q, torch.bfloat16, 3, "Q")
+    cand = _need(cand, torch.int64, 2, "cand")
+    if doclen is not None:
+        doclen = _need(doclen, torch.int32, 1, "doclen")
+    Nd, Ld, dim = D.shape
+    nq, Lq, _ = Q.shape
+    C = cand.shape[1]
+    s, i = _out(nq, k, D.device)
+    ws = _ws(lib.lrag_maxsim_rerank_workspace_bytes(nq, C, k), D.device)
+    rc = lib.lrag_maxsim_rerank_bf16(_ptr(D), _ptr(doclen), Nd, Ld, dim, _ptr(Q), nq, Lq, _ptr(cand), C, k, id_base,
+                                     _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+    check(rc, "lrag_maxsim_rerank_bf16")
+    return s, i
+
+
+# ------------------------------------------------------------------------------------------------
+# fusion
+# ------------------------------------------------------------------------------------------------
+def fuse_topk(dense=None, bm25=None, colbert=None, *, k: int, method: str = "rrf_norm_blend",
+              w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, rrf_k: int = 60,
+              alpha: float = 0.5, min_final: float = float("-inf"), breakdown: bool = False):
+    """Each channel is None or (scores [nq, kc] f32, ids [nq, kc] i64) sorted (score desc), -1 padded at
+    the tail.  Returns (scores, ids[, breakdown [nq, k, 8]])."""
+    chans = [dense, bm25, colbert]
+    first = next((c for c in chans if c is not None), None)
+    if first is None:
+        raise LragError("fuse_topk: all channels are empty")
+    dev = first[0].device
+    lib = _native.init(dev.index)
+    nq = first[0].shape[0]
+    kc = max(c[0].shape[1] for c in chans if c is not None)
+    ptrs = []
+    keep = []
+    for c in chans:
+        if c is None:
+            ptrs += [None, None]
+            continue
+        s = _need(c[0], torch.float32, 2, "channel scores")
+        i = _need(c[1], torch.int64, 2, "channel ids")
+        if s.shape[1] < kc:   # ragged channel widths: pad at the tail
+            pad = kc - s.shape[1]
+            s = torch.nn.functional.pad(s, (0, pad), value=PAD_SCORE)
+            i = torch.nn.functional.pad(i, (0, pad), value=-1)
+        keep += [s, i]
+        ptrs += [_ptr(s), _ptr(i)]
+    if method.lower() not in FUSION_METHODS:
+        method = "rrf_norm_blend"   # hybrid_retriever.py:516-523: unknown names fall through to the blend
+    s, i = _out(nq, k, dev)
+    bd = torch.empty((nq, k, 8), dtype=torch.float32, device=dev) if breakdown else None
+    rc = lib.lrag_fuse_topk(*ptrs, nq, kc, k, FUSION_METHODS[method.lower()], float(w_dense), float(w_bm25),
+                            float(w_colbert), int(rrf_k), float(alpha), float(min_final), _ptr(s), _ptr(i), _ptr(bd), _stream())
+    check(rc, "lrag_fuse_topk")
+    return (s, i, bd) if breakdown else (s, i)
+
+
+# ------------------------------------------------------------------------------------------------
+# launch profiler (bench.py's roofline leg)
+# ------------------------------------------------------------------------------------------------
+PROF_TAGS = {0: "dense_scan", 1: "bm25_scan", 2: "maxsim", 3: "fuse"}
+
+
+def prof_enable(capacity: int) -> None:
+    check(_native.init().lrag_prof_enable(int(capacity)), "lrag_prof_enable")
+
+
+def prof_collect(max_n: int = 4096):
+    """-> list of (kernel name, milliseconds) for the tagged launches since the last collect."""
+    import ctypes as C
+    ms = (C.c_float * max_n)()
+    tag = (C.c_int * max_n)()
+    n = _native.init().lrag_prof_collect(ms, tag, max_n)
+    if n < 0:
+        check(n, "lrag_prof_collect")
+    return [(PROF_TAGS.get(tag[j], str(tag[j])), float(ms[j])) for j in range(n)]
+
+
+# ------------------------------------------------------------------------------------------------
+# shards: one process per GPU owns a contiguous doc-id range of every channel
+# ------------------------------------------------------------------------------------------------
+def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous doc-id range [lo, hi) owned by `rank`."""
+    per = (n_total + world - 1) // world
+    lo = min(n_total, rank * per)
+    return lo, min(n_total, lo + per)
+
+
+def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None):
+    """The one exchange step of the sharded path: all-gather each rank's local top-k (global ids) over
+    NCCL (gloo on CPU tensors in tests) and k-way merge, replicated on every rank."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return scores, ids
+    world = dist.get_world_size(group)
+    nq = scores.shape[0]
+    gs = torch.empty((world, nq, k), dtype=scores.dtype, device=scores.device)
+    gi = torch.empty((world, nq, k), dtype=ids.dtype, device=ids.device)
+    dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
+    dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    cat_s = gs.permute(1, 0, 2).reshape(nq, world * k).contiguous()
+    cat_i = gi.permute(1, 0, 2).reshape(nq, world * k).contiguous()
+    return topk_merge(cat_s, cat_i, k)
+
+
+class FlatIPShard:
+    """Device-resident bf16 corpus shard [N, d] with the faiss-shaped batched search entry point:
+    search(Q) with Q on the HOST (pinned) does H2D -> scan -> (all-gather merge) -> D2H."""
+
+    def __init__(self, X: torch.Tensor, id_base: int = 0, group=None):
+        self.X = _need(X, torch.bfloat16, 2, "X")
+        self.id_base = int(id_base)
+        self.group = group
+        self._qbuf = None
+        self._out = None
+
+    @property
+    def ntotal(self) -> int:
+        return int(self.X.shape[0])
+
+    @property
+    def d(self) -> int:
+        return int(self.X.shape[1])
+
+    def search_device(self, Q: torch.Tensor, k: int):
+        s, i = dense_topk(self.X, Q, k, self.id_base)
+        return allgather_merge(s, i, k, self.group)
+
+    def search(self, Q_host: torch.Tensor, k: int):
+        """Q_host: [nq, d] float32 or bf16 CPU tensor (pinned for async copies).  Returns CPU
+        (D float32 [nq, k], I int64 [nq, k]) like faiss index.search (dense_retriever.py:42)."""
+        dev = self.X.device
+        nq = Q_host.shape[0]
+        if self._qbuf is None or self._qbuf.shape[0] < nq or self._qbuf.dtype != Q_host.dtype:
+            self._qbuf = torch.empty((nq, self.d), dtype=Q_host.dtype, device=dev)
+        qd = self._qbuf[:nq]
+        qd.copy_(Q_host, non_blocking=True)
+        s, i = self.search_device(qd if qd.dtype == torch.bfloat16 else qd.to(torch.bfloat16), k)
+        if self._out is None or self._out[0].shape != s.shape:
+            self._out = (torch.empty(s.shape, dtype=s.dtype, pin_memory=True), torch.empty(i.shape, dtype=i.dtype, pin_memory=True))
+        self._out[0].copy_(s, non_blocking=True)
+        self._out[1].copy_(i, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._out

@@ -1,0 +1,78 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, and exports exactly what
+include/lrag.h declares; the ctypes binding covers every declared function; and nothing on the
+product side imports the oracle or falls back to a CPU path."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    with open(os.path.join(ROOT, "include", "lrag.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(lrag_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from legal_rag_b200 import build
+    return str(build.build_native())
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared()
+    for must in ("lrag_init", "lrag_dense_topk_bf16", "lrag_bm25_topk", "lrag_maxsim_rerank_bf16", "lrag_fuse_topk",
+                 "lrag_topk_merge", "lrag_topk_select_f32"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    missing = [n for n in _declared() if n not in exported]
+    assert not missing, missing
+    lib = ctypes.CDLL(lib_path)
+    for n in _declared():
+        assert getattr(lib, n) is not None
+
+
+def test_ctypes_binding_covers_the_header(lib_path):
+    from legal_rag_b200 import _native
+    assert sorted(_native.SIGNATURES) == _declared()
+    lib = _native.load()
+    assert lib.lrag_version() == 100
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma(lib_path):
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass or "UTCMMA" in sass, "no tcgen05.mma in the SASS"
+    assert "LDTM" in sass, "no tcgen05.ld in the SASS"
+    assert "UTMALDG" in sass, "no TMA tensor loads in the SASS"
+
+
+def test_init_without_a_gpu_fails_loudly(lib_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from legal_rag_b200 import _native, engine
+    with pytest.raises(_native.LragError, match="no CUDA device|CPU fallback"):
+        _native.init()
+    with pytest.raises(RuntimeError):
+        engine.dense_topk(torch.zeros((4, 64), dtype=torch.bfloat16), torch.zeros((1, 64), dtype=torch.bfloat16), 2)
+
+
+def test_product_code_never_touches_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "legal_rag_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn), encoding="utf-8") as f:
+                    src = f.read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src and fn.endswith(".py"):
+                    bad.append(fn)
+    assert not bad, bad
