@@ -211,7 +211,7 @@ bm25_scan_kernel(const Bm25Params p) {
       // ---- 3. scan the slab for candidates ----
       const int cnt_before = sh.cand_cnt;
       const unsigned long long thr_key = sh.thr_key;
-      const float thr_s = key_score(thr_key);
+      const float thr_s = thr_key ? key_score(thr_key) : -INFINITY;
       __syncthreads();   // everyone has read cand_cnt before anyone appends
       {
         const float4* a4 = reinterpret_cast<const float4*>(acc);

@@ -119,7 +119,8 @@ fuse_kernel(const FuseParams p) {
     if (p.method == 0) s = wsum[e];
     else if (p.method == 3) s = p.alpha * rn + (1.0 - p.alpha) * wsum[e];
     else s = rn;
-    if (s >= p.min_final) score[e] = s;
+    // rank on the value that is returned (fp32), so equal outputs are ordered by id
+    if (s >= p.min_final) score[e] = double(float(s));
   }
   __syncthreads();
   // ---- bitonic sort of entry indices by (score desc, id asc); dropped entries sink ----

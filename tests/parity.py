@@ -11,8 +11,12 @@ from __future__ import annotations
 import numpy as np
 
 
-def check_topk_parity(prod_s, prod_i, orc_s, orc_i, k, tau, what=""):
-    """prod_*: [nq, k]; orc_*: [nq, >=k] (pass k + margin so the cut can be judged)."""
+def check_topk_parity(prod_s, prod_i, orc_s, orc_i, k, tau, what="", floor=1e-6):
+    """prod_*: [nq, k]; orc_*: [nq, >=k] (pass k + margin so the cut can be judged).
+
+    `floor`: scores smaller in magnitude than this are compared as if they had this magnitude
+    (tolerance tau * max(|s|, floor)).  bf16-vs-fp32 comparisons of cosine scores use 0.1: input
+    rounding perturbs a dot product of unit vectors by an amount that does not shrink with |s|."""
     prod_s = np.asarray(prod_s, dtype=np.float64)
     prod_i = np.asarray(prod_i)
     orc_s = np.asarray(orc_s, dtype=np.float64)
@@ -31,7 +35,7 @@ def check_topk_parity(prod_s, prod_i, orc_s, orc_i, k, tau, what=""):
         a = 0
         while a < kk:
             b = a + 1
-            while b < valid and (os_[b - 1] - os_[b]) <= tau * max(abs(os_[b - 1]), 1e-6):
+            while b < valid and (os_[b - 1] - os_[b]) <= tau * max(abs(os_[b - 1]), floor):
                 b += 1
             run_ids = set(int(x) for x in oi[a:b])
             got = [int(x) for x in pi[a:min(b, kk)]]
@@ -49,14 +53,14 @@ def check_topk_parity(prod_s, prod_i, orc_s, orc_i, k, tau, what=""):
                         continue
                     assert exhausted, f"{what} q={q} run [{a},{b}) crossing k: id {g} not in oracle run"
                     # oracle list ran out inside the tie run: judge by score only
-                    assert ps[a + j] >= os_[valid - 1] - tau * max(abs(os_[valid - 1]), 1e-6), \
+                    assert ps[a + j] >= os_[valid - 1] - tau * max(abs(os_[valid - 1]), floor), \
                         f"{what} q={q}: id {g} score {ps[a+j]} below oracle tail {os_[valid-1]}"
             a = b
         for j in range(kk):
             g = int(pi[j])
             if g in score_of:
                 ref = score_of[g]
-                assert abs(ps[j] - ref) <= tau * max(abs(ref), 1e-6) + 1e-12, \
+                assert abs(ps[j] - ref) <= tau * max(abs(ref), floor) + 1e-12, \
                     f"{what} q={q} pos={j} id={g}: score {ps[j]} vs oracle {ref} (tau={tau})"
         # returned list must be sorted (score desc, id asc)
         for j in range(1, kk):

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Runs the GPU parity suites one process per kernel family (a faulting kernel poisons its CUDA
+# context, so families are isolated), then a short bench.  Logs land in gpurun_out/.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+run() {  # name, -k expression
+  echo "=== $1" | tee -a gpurun_out/tests.log
+  timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "$2" > gpurun_out/test_$1.log 2>&1
+  echo "exit $? : $(tail -1 gpurun_out/test_$1.log)" | tee -a gpurun_out/tests.log
+}
+run select "topk_select or topk_merge"
+run fuse "fuse"
+run bm25 "bm25"
+run dense_ref "dense_cuda_core"
+run maxsim "maxsim"
+run dense "dense_tcgen05 or dense_duplicate or dense_rejects"
