@@ -61,6 +61,8 @@ int lrag_sm_count(void);
  * lrag_prof_enable(0) switches it off.  Single-threaded use only. */
 int lrag_prof_enable(int capacity);
 int lrag_prof_collect(float* ms, int* tag, int max_n);
+/* cumulative number of kernels this library has launched in the process (bench.py's gpu_launches) */
+long long lrag_launch_count(void);
 
 /* ---------------------------------------------------------------------------------
  * Dense channel.  Replaces faiss `index.search(q_vec, k)` at

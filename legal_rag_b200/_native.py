@@ -29,6 +29,7 @@ SIGNATURES = {
     "lrag_sm_count": (_c_int, []),
     "lrag_prof_enable": (_c_int, [_c_int]),
     "lrag_prof_collect": (_c_int, [_c_p, _c_p, _c_int]),
+    "lrag_launch_count": (C.c_longlong, []),
     "lrag_dense_topk_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
     "lrag_dense_topk_bf16": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_dense_topk_ref_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),

@@ -379,9 +379,9 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   prof_begin(stream, PROF_BM25_SCAN);
   bm25_scan_kernel<<<unsigned(int64_t(nq) * pl.nsplit), BM25_THREADS, pl.smem, stream>>>(p);
   prof_end(stream);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   bm25_merge_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p.out_keys, pl.nsplit, k, pl.P, N, id_base,
                                                                           p.nonneg, out_score, out_id);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }

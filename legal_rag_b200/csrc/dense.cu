@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "select.cuh"
 
+#include <cstdlib>
+
 namespace lrag {
 
 constexpr int DENSE_BM = 128;          // queries per tile (UMMA M)
@@ -36,15 +38,19 @@ struct DenseParams {
   int g;             // gcd(grid, QB): CTA c only ever sees query blocks == c (mod g)
   int slots;         // (QB / g) * 128 candidate buffers per CTA
   int cap;           // entries per candidate buffer
+  int debug;         // 0 normal; 1 = TMA only (no MMA, no epilogue); 2 = TMA + MMA, epilogue skipped (timing experiments)
   uint32_t* thr;     // [QB*128] orderable k-th best score so far, per query
   int32_t* cnt;      // [grid * slots]
   uint64_t* buf;     // [grid * slots * cap]
+  uint64_t* best;    // [nq * k] keys: each query's exact top-k over the epochs already tightened (0 = empty)
+  int64_t t_begin, t_end;   // tile range of this launch (one epoch)
 };
 
-__global__ void dense_init_kernel(uint32_t* thr, int nthr, int32_t* cnt, int ncnt) {
+__global__ void dense_init_kernel(uint32_t* thr, int nthr, int32_t* cnt, int ncnt, uint64_t* best, int nbest) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nthr) thr[i] = LRAG_ORD_NEG_INF;
   if (i < ncnt) cnt[i] = 0;
+  if (i < nbest) best[i] = 0;
 }
 
 __global__ void __launch_bounds__(DENSE_THREADS, 1)
@@ -62,7 +68,6 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = (p.d + DENSE_BK - 1) / DENSE_BK;
-  const int64_t num_tiles = p.DT * p.QB;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -81,7 +86,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int64_t t = p.t_begin + blockIdx.x; t < p.t_end; t += gridDim.x) {
         const int qb = int(t % p.QB);
         const int64_t dt = t / p.QB;
         for (int kb = 0; kb < KB; ++kb) {
@@ -101,7 +106,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       constexpr uint32_t idesc = umma_idesc_bf16(DENSE_BM, DENSE_BN);
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int64_t t = p.t_begin + blockIdx.x; t < p.t_end; t += gridDim.x, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -113,67 +118,109 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           const uint32_t b_addr = a_addr + DENSE_A_BYTES;
           const uint64_t da = umma_desc_k_sw128(a_addr);
           const uint64_t db = umma_desc_k_sw128(b_addr);
+          if (p.debug == 1) {
+            mbar_arrive(&empty_bar[stage]);
+            if (kb == KB - 1) mbar_arrive(&tfull_bar[as]);
+          } else {
 #pragma unroll
-          for (int kk = 0; kk < DENSE_BK / 16; ++kk) {
-            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16 B units
-            umma_bf16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc,
-                         (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < DENSE_BK / 16; ++kk) {
+              // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16 B units
+              umma_bf16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc,
+                           (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
+            if (kb == KB - 1) umma_commit(&tfull_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);            // smem slot reusable once these MMAs retire
-          if (kb == KB - 1) umma_commit(&tfull_bar[as]);
           if (++stage == DENSE_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
     // ===================== epilogue: threshold filter out of TMEM =====================
+    // Per 32-column chunk the common case is "nothing beats the threshold": one tcgen05.ld, a max
+    // tree and one vote.  Only lanes whose chunk max reaches the threshold walk their columns.
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     const int cap = p.cap;
     uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    // this tile's counter / threshold are fetched one tile ahead (their L2 latency would otherwise
+    // sit on the critical path of every tile)
+    int64_t t = p.t_begin + blockIdx.x;
+    size_t sidx_n = 0; int q_n = 0; int cnt_n = 0; uint32_t thr_n = LRAG_ORD_NEG_INF;
+    if (t < p.t_end) {
       const int qb = int(t % p.QB);
+      q_n = qb * DENSE_BM + row;
+      sidx_n = size_t(blockIdx.x) * p.slots + (qb / p.g) * DENSE_BM + row;
+      cnt_n = p.cnt[sidx_n];
+      thr_n = *reinterpret_cast<volatile uint32_t*>(&p.thr[q_n]);
+    }
+    for (; t < p.t_end; t += gridDim.x, ++it) {
       const int64_t dt = t / p.QB;
-      const int q = qb * DENSE_BM + row;
+      const int q = q_n;
+      const size_t sidx = sidx_n;
       const bool qvalid = q < p.nq;
-      const int slot = (qb / p.g) * DENSE_BM + row;
-      const size_t sidx = size_t(blockIdx.x) * p.slots + slot;
       uint64_t* mybuf = p.buf + sidx * cap;
-      int cnt = p.cnt[sidx];
+      int cnt = cnt_n;
       const int cnt0 = cnt;
-      float thr = unord32(*reinterpret_cast<volatile uint32_t*>(&p.thr[q]));
+      float thr = unord32(thr_n);
       const int64_t n0 = dt * DENSE_BN;
+      const bool tail = n0 + DENSE_BN > p.N;        // only the last doc tile holds out-of-range columns
+      const int64_t tn = t + gridDim.x;
+      if (tn < p.t_end) {
+        const int qb = int(tn % p.QB);
+        q_n = qb * DENSE_BM + row;
+        sidx_n = size_t(blockIdx.x) * p.slots + (qb / p.g) * DENSE_BM + row;
+        if (sidx_n != sidx) cnt_n = p.cnt[sidx_n];
+        thr_n = *reinterpret_cast<volatile uint32_t*>(&p.thr[q_n]);
+      }
 
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * DENSE_BN;
 #pragma unroll 1
-      for (int c = 0; c < DENSE_BN / 32; ++c) {
+      for (int c = 0; c < (p.debug ? 0 : DENSE_BN / 32); ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
-        const int64_t nbase = n0 + c * 32;
-        if (qvalid) {
+        float m8[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = __uint_as_float(v[j]);
-            if (s >= thr && nbase + j < p.N) mybuf[cnt++] = make_key(s, uint32_t(nbase + j));
-          }
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float m = __uint_as_float(v[g8 * 8]);
+#pragma unroll
+          for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[g8 * 8 + j]));
+          m8[g8] = m;
         }
-        // a buffer that could overflow in the next chunk is cut back to its k best, warp-wide
-        uint32_t m = __ballot_sync(0xffffffffu, cnt > cap - 32);
-        while (m) {
-          const int L = __ffs(m) - 1;
-          m &= m - 1;
-          uint64_t* bufL = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mybuf), L));
-          const int nL = __shfl_sync(0xffffffffu, cnt, L);
-          const uint64_t pivot = warp_keep_topk(bufL, nL, p.k, lane);
-          if (lane == L) {
-            cnt = p.k;
-            const uint32_t o = uint32_t(pivot >> 32);
-            atomicMax(&p.thr[q], o);
-            thr = fmaxf(thr, unord32(o));
+        const bool hit = qvalid && fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])) >= thr;
+        if (__any_sync(0xffffffffu, hit)) {
+          if (hit) {
+            const int64_t nbase = n0 + c * 32;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              if (m8[g8] >= thr) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float sc = __uint_as_float(v[g8 * 8 + j]);
+                  const int64_t n = nbase + g8 * 8 + j;
+                  if (sc >= thr && (!tail || n < p.N)) mybuf[cnt++] = make_key(sc, uint32_t(n));
+                }
+              }
+            }
+          }
+          // a buffer that could overflow in the next chunk is cut back to its k best, warp-wide
+          uint32_t m = __ballot_sync(0xffffffffu, cnt > cap - 32);
+          while (m) {
+            const int L = __ffs(m) - 1;
+            m &= m - 1;
+            uint64_t* bufL = reinterpret_cast<uint64_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mybuf), L));
+            const int nL = __shfl_sync(0xffffffffu, cnt, L);
+            const uint64_t pivot = warp_keep_topk(bufL, nL, p.k, lane);
+            if (lane == L) {
+              cnt = p.k;
+              const uint32_t o = uint32_t(pivot >> 32);
+              atomicMax(&p.thr[q], o);
+              thr = fmaxf(thr, unord32(o));
+            }
           }
         }
       }
@@ -181,6 +228,10 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (cnt != cnt0) p.cnt[sidx] = cnt;
+      if (tn < p.t_end) {
+        if (sidx_n == sidx) cnt_n = cnt;                                   // same buffer again next tile
+        if (q_n == q) thr_n = max(thr_n, ord32(thr));                      // keep a locally raised threshold
+      }
     }
   }
 
@@ -194,9 +245,10 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
 // ---- exact top-k over each query's surviving candidates ----
 struct DenseSegments {
-  const uint64_t* buf; const int32_t* cnt;
-  int grid, g, slots, cap, first_cta, slot;
+  const uint64_t* buf; const int32_t* cnt; const uint64_t* best;
+  int grid, g, slots, cap, first_cta, slot, k;
   template <class F> __device__ void operator()(F&& f) const {
+    for (int i = threadIdx.x; i < k; i += SELECT_THREADS) { const uint64_t key = best[i]; if (key) f(key); }
     for (int c = first_cta; c < grid; c += g) {
       const size_t sidx = size_t(c) * slots + slot;
       const int n = cnt[sidx];
@@ -206,6 +258,10 @@ struct DenseSegments {
   }
 };
 
+// FINAL: write (score, id) rows.  Otherwise ("tighten", between epochs): fold every CTA's candidates
+// into best[q], raise thr[q] to the exact k-th best score seen so far and empty the CTA buffers, so
+// that the next epoch filters against the global threshold instead of each CTA's local one.
+template <bool FINAL>
 __global__ void __launch_bounds__(SELECT_THREADS)
 dense_finalize_kernel(DenseParams p, int grid, int64_t id_base, int P, float* out_score, int64_t* out_id) {
   extern __shared__ uint8_t sm_raw[];
@@ -213,16 +269,26 @@ dense_finalize_kernel(DenseParams p, int grid, int64_t id_base, int P, float* ou
   uint64_t* sel_key = reinterpret_cast<uint64_t*>(sm_raw);
   const int q = blockIdx.x;
   const int qb = q / DENSE_BM, row = q % DENSE_BM;
-  DenseSegments seg{p.buf, p.cnt, grid, p.g, p.slots, p.cap, qb % p.g, (qb / p.g) * DENSE_BM + row};
-  block_topk_sorted(seg, p.k, P, ss, sel_key, id_base, out_score + size_t(q) * p.k, out_id + size_t(q) * p.k,
-                    static_cast<uint64_t*>(nullptr));
+  uint64_t* best = p.best + size_t(q) * p.k;
+  DenseSegments seg{p.buf, p.cnt, best, grid, p.g, p.slots, p.cap, qb % p.g, (qb / p.g) * DENSE_BM + row, p.k};
+  if (FINAL) {
+    block_topk_sorted(seg, p.k, P, ss, sel_key, id_base, out_score + size_t(q) * p.k, out_id + size_t(q) * p.k,
+                      static_cast<uint64_t*>(nullptr));
+  } else {
+    const int n = block_topk_sorted(seg, p.k, P, ss, sel_key, 0, static_cast<float*>(nullptr),
+                                    static_cast<int64_t*>(nullptr), best);
+    if (threadIdx.x == 0 && n >= p.k) atomicMax(&p.thr[q], uint32_t(sel_key[p.k - 1] >> 32));
+    for (int c = seg.first_cta + p.g * threadIdx.x; c < grid; c += p.g * SELECT_THREADS)
+      p.cnt[size_t(c) * p.slots + seg.slot] = 0;
+  }
 }
 
 static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 struct DensePlan {
   int grid, QB, g, slots, cap; int64_t DT;
-  size_t off_thr, off_cnt, off_buf, total;
+  size_t off_thr, off_cnt, off_best, off_buf, total;
+  int64_t epoch0;    // tiles in the first epoch (a multiple of lcm(grid, QB)); later epochs grow 4x
 };
 
 static DensePlan dense_plan(int64_t N, int nq, int k, int sms) {
@@ -238,7 +304,9 @@ static DensePlan dense_plan(int64_t N, int nq, int k, int sms) {
   if (pl.cap < 128) pl.cap = 128;
   pl.off_thr = 0;
   pl.off_cnt = align_up(size_t(pl.QB) * DENSE_BM * 4, 256);
-  pl.off_buf = pl.off_cnt + align_up(size_t(pl.grid) * pl.slots * 4, 256);
+  pl.off_best = pl.off_cnt + align_up(size_t(pl.grid) * pl.slots * 4, 256);
+  pl.off_buf = pl.off_best + align_up(size_t(pl.QB) * DENSE_BM * k * 8, 256);
+  pl.epoch0 = int64_t(pl.grid) / pl.g * pl.QB;
   pl.total = pl.off_buf + size_t(pl.grid) * pl.slots * pl.cap * 8;
   return pl;
 }
@@ -268,17 +336,22 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
   if (ws_bytes < pl.total || !ws) { set_error("dense_topk: workspace %zu < required %zu", ws_bytes, pl.total); return LRAG_ENOSPC; }
 
   DenseParams p;
+  { const char* dbg = getenv("LRAG_DENSE_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.N = N; p.nq = nq; p.d = d; p.k = k; p.QB = pl.QB; p.DT = pl.DT; p.g = pl.g; p.slots = pl.slots; p.cap = pl.cap;
   uint8_t* w = static_cast<uint8_t*>(ws);
   p.thr = reinterpret_cast<uint32_t*>(w + pl.off_thr);
   p.cnt = reinterpret_cast<int32_t*>(w + pl.off_cnt);
   p.buf = reinterpret_cast<uint64_t*>(w + pl.off_buf);
+  p.best = reinterpret_cast<uint64_t*>(w + pl.off_best);
+  p.t_begin = 0; p.t_end = 0;
 
-  const int nthr = pl.QB * DENSE_BM, ncnt = pl.grid * pl.slots;
-  const int ninit = nthr > ncnt ? nthr : ncnt;
-  dense_init_kernel<<<(ninit + 255) / 256, 256, 0, stream>>>(p.thr, nthr, p.cnt, ncnt);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  const int nthr = pl.QB * DENSE_BM, ncnt = pl.grid * pl.slots, nbest = nq * k;
+  int ninit = nthr > ncnt ? nthr : ncnt;
+  if (nbest > ninit) ninit = nbest;
+  dense_init_kernel<<<(ninit + 255) / 256, 256, 0, stream>>>(p.thr, nthr, p.cnt, ncnt, p.best, nbest);
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
 
+  const int P = next_pow2(k);
   if (N > 0) {
     CUtensorMap tq, tx;
     int rc = make_tmap_bf16_2d(&tq, Q, uint64_t(nq), uint64_t(d), uint64_t(d), DENSE_BM, DENSE_BK);
@@ -290,14 +363,30 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
       LRAG_CHECK_CUDA(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
       attr_set = true;
     }
-    prof_begin(stream, PROF_DENSE_SCAN);
-    dense_scan_kernel<<<pl.grid, DENSE_THREADS, DENSE_SMEM, stream>>>(tq, tx, p);
-    prof_end(stream);
-    LRAG_CHECK_CUDA(cudaGetLastError());
+    // Epochs: [0, e0), [e0, 4 e0), [4 e0, 16 e0), ... ; between two epochs every query's threshold is
+    // tightened to its exact k-th best so far.  An epoch boundary is a multiple of lcm(grid, QB) tiles,
+    // which keeps each CTA on the same residue class of query blocks (its slot map) in every epoch.
+    const int64_t num_tiles = pl.DT * pl.QB;
+    int64_t t0 = 0, span = pl.epoch0;
+    const bool epochs = !getenv("LRAG_DENSE_ONE_EPOCH");
+    while (t0 < num_tiles) {
+      int64_t t1 = t0 + span;
+      if (!epochs || t1 + span / 2 >= num_tiles) t1 = num_tiles;     // do not leave a sliver for the last launch
+      p.t_begin = t0; p.t_end = t1;
+      prof_begin(stream, PROF_DENSE_SCAN);
+      dense_scan_kernel<<<pl.grid, DENSE_THREADS, DENSE_SMEM, stream>>>(tq, tx, p);
+      prof_end(stream);
+      LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+      if (t1 < num_tiles) {
+        dense_finalize_kernel<false><<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p, pl.grid, id_base, P, nullptr, nullptr);
+        LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+      }
+      span = (t1 - 0) * 3;      // next epoch is three times everything scanned so far (4x growth)
+      t0 = t1;
+    }
   }
-  const int P = next_pow2(k);
-  dense_finalize_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p, pl.grid, id_base, P, out_score, out_id);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  dense_finalize_kernel<true><<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p, pl.grid, id_base, P, out_score, out_id);
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }
 
@@ -345,7 +434,7 @@ extern "C" int lrag_dense_topk_bf16_ref(const void* X, int64_t N, int d, const v
     dim3 grid(unsigned((N + 255) / 256), unsigned(nq));
     dense_scores_ref_kernel<<<grid, 256, size_t(d) * 4, stream>>>(static_cast<const __nv_bfloat16*>(X), N, d,
                                                                   static_cast<const __nv_bfloat16*>(Q), S);
-    LRAG_CHECK_CUDA(cudaGetLastError());
+    LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   }
   return launch_topk_select(S, N, nq, N, k, id_base, nullptr, out_score, out_id, stream);
 }

@@ -211,6 +211,6 @@ extern "C" int lrag_fuse_topk(const float* s_dense, const int64_t* i_dense, cons
   prof_begin(static_cast<cudaStream_t>(stream), PROF_FUSE);
   fuse_kernel<<<nq, FUSE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);
   prof_end(static_cast<cudaStream_t>(stream));
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }

@@ -225,7 +225,7 @@ static int maxsim_launch(const void* D, const int32_t* doclen, int64_t Nd, int L
   prof_begin(stream, PROF_MAXSIM);
   maxsim_kernel<<<grid, MS_THREADS, smem, stream>>>(tq, td, p);
   prof_end(stream);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }
 

@@ -59,7 +59,7 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
   const int P = next_pow2(k);
   topk_select_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(S, ld, N, k, id_base, col_id, P, out_score,
                                                                            out_id);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }
 
@@ -93,6 +93,6 @@ extern "C" int lrag_topk_merge(const float* score, const int64_t* id, int nq, in
   const int P = next_pow2(k);
   topk_merge_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), static_cast<cudaStream_t>(stream)>>>(
       score, id, L, k, P, out_score, out_id);
-  LRAG_CHECK_CUDA(cudaGetLastError());
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;
 }

@@ -232,6 +232,11 @@ def prof_enable(capacity: int) -> None:
     check(_native.init().lrag_prof_enable(int(capacity)), "lrag_prof_enable")
 
 
+def launch_count() -> int:
+    """Kernels launched by liblrag in this process so far."""
+    return int(_native.load().lrag_launch_count())
+
+
 def prof_collect(max_n: int = 4096):
     """-> list of (kernel name, milliseconds) for the tagged launches since the last collect."""
     import ctypes as C
