@@ -87,6 +87,47 @@ struct Bm25Union {
   }
 };
 
+// One batch of one (slab, term) pair: postings [pos, min(pos + BATCH, hi)) of term t in slab j of the
+// current slab group.  t < 0 = no more work in this group.
+struct Bm25Cursor { int t, j, pos, hi; };
+constexpr int BM25_BATCH_POSTINGS = BM25_THREADS * BM25_UNROLL;
+
+__device__ __forceinline__ Bm25Cursor bm25_seek(const Bm25Shared& sh, int nt, int t, int j, int64_t b0, int64_t range_end,
+                                                int nonneg) {
+  for (; j < BM25_BATCH && b0 + int64_t(j) * BM25_SLAB < range_end; ++j, t = 0) {
+    if (nonneg && !sh.slab_any[j]) continue;
+    for (; t < nt; ++t)
+      if (sh.bound[t][j + 1] > sh.bound[t][j]) return Bm25Cursor{t, j, sh.bound[t][j], sh.bound[t][j + 1]};
+  }
+  return Bm25Cursor{-1, BM25_BATCH, 0, 0};
+}
+__device__ __forceinline__ Bm25Cursor bm25_first(const Bm25Shared& sh, int nt, int64_t b0, int64_t range_end, int nonneg) {
+  return bm25_seek(sh, nt, 0, 0, b0, range_end, nonneg);
+}
+__device__ __forceinline__ Bm25Cursor bm25_next(const Bm25Shared& sh, int nt, const Bm25Cursor& c, int64_t b0, int64_t range_end,
+                                               int nonneg) {
+  if (c.pos + BM25_BATCH_POSTINGS < c.hi) return Bm25Cursor{c.t, c.j, c.pos + BM25_BATCH_POSTINGS, c.hi};
+  return bm25_seek(sh, nt, c.t + 1, c.j, b0, range_end, nonneg);
+}
+// issue this thread's loads of a batch (doc id < 0 marks an empty lane)
+__device__ __forceinline__ void bm25_load(const Bm25Params& p, const Bm25Shared& sh, const Bm25Cursor& c, int tid,
+                                          int (&d)[BM25_UNROLL], float (&v)[BM25_UNROLL]) {
+  if (c.t < 0) {
+#pragma unroll
+    for (int u = 0; u < BM25_UNROLL; ++u) { d[u] = -1; v[u] = 0.f; }
+    return;
+  }
+  const int32_t* __restrict__ ids = p.doc_id + sh.t_start[c.t];
+  const float* __restrict__ imp = p.impact + sh.t_start[c.t];
+#pragma unroll
+  for (int u = 0; u < BM25_UNROLL; ++u) {
+    const int ii = c.pos + tid + u * BM25_THREADS;
+    const bool ok = ii < c.hi;
+    d[u] = ok ? __ldg(ids + ii) : -1;
+    v[u] = ok ? __ldg(imp + ii) : 0.f;
+  }
+}
+
 struct Bm25Cands {
   const uint64_t* c; int n;
   template <class F> __device__ void operator()(F&& f) const {
@@ -151,6 +192,12 @@ bm25_scan_kernel(const Bm25Params p) {
   if (tid < nt) sh.t_cur[tid] = lower_bound_doc(p.doc_id + sh.t_start[tid], 0, sh.t_len[tid], range_begin);
   __syncthreads();
 
+  {
+    float4* a4 = reinterpret_cast<float4*>(acc);
+#pragma unroll
+    for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) a4[tid + i * BM25_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
   const int64_t batch_docs = int64_t(BM25_SLAB) * BM25_BATCH;
   for (int64_t b0 = range_begin; b0 < range_end; b0 += batch_docs) {
     // ---- 1. posting boundaries for the next BM25_BATCH slabs ----
@@ -172,61 +219,65 @@ bm25_scan_kernel(const Bm25Params p) {
     if (tid < nt) sh.t_cur[tid] = sh.bound[tid][BM25_BATCH];
     __syncthreads();
 
+    // ---- 2. per slab: pipelined term-at-a-time accumulation, scan, re-zero ----
+    // The postings of a (slab, term) pair are consumed in batches of BM25_THREADS * BM25_UNROLL; the
+    // loads of the NEXT batch (possibly of the next term or the next slab) are issued before the
+    // current batch is added, so the HBM latency of one batch hides behind the shared-memory work
+    // and the barrier of the previous one.
+    Bm25Cursor cur = bm25_first(sh, nt, b0, range_end, p.nonneg);
+    int d_cur[BM25_UNROLL]; float v_cur[BM25_UNROLL];
+    bm25_load(p, sh, cur, tid, d_cur, v_cur);
     for (int j = 0; j < BM25_BATCH; ++j) {
       const int64_t slab0 = b0 + int64_t(j) * BM25_SLAB;
       if (slab0 >= range_end) break;
       if (p.nonneg && !sh.slab_any[j]) continue;
-      // ---- 2a. zero the slab ----
-      {
-        float4* a4 = reinterpret_cast<float4*>(acc);
+      const int sl0 = int(slab0);   // doc ids are int32
+      while (cur.t >= 0 && cur.j == j) {
+        const Bm25Cursor nxt = bm25_next(sh, nt, cur, b0, range_end, p.nonneg);
+        int d_nxt[BM25_UNROLL]; float v_nxt[BM25_UNROLL];
+        bm25_load(p, sh, nxt, tid, d_nxt, v_nxt);
+        const float mult = sh.t_mult[cur.t];
+        float a[BM25_UNROLL];
 #pragma unroll
-        for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) a4[tid + i * BM25_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < BM25_UNROLL; ++u) a[u] = (d_cur[u] >= 0) ? acc[d_cur[u] - sl0] : 0.f;
+#pragma unroll
+        for (int u = 0; u < BM25_UNROLL; ++u) if (d_cur[u] >= 0) acc[d_cur[u] - sl0] = fmaf(mult, v_cur[u], a[u]);
+        // same-term batches never touch the same doc: a barrier is only needed when the term changes
+        if (nxt.t != cur.t || nxt.j != j) __syncthreads();
+        cur = nxt;
+#pragma unroll
+        for (int u = 0; u < BM25_UNROLL; ++u) { d_cur[u] = d_nxt[u]; v_cur[u] = v_nxt[u]; }
       }
-      __syncthreads();
-      // ---- 2b. term-at-a-time accumulation ----
-      for (int t = 0; t < nt; ++t) {
-        const int lo = sh.bound[t][j], hi = sh.bound[t][j + 1];
-        if (lo == hi) continue;
-        const int32_t* __restrict__ ids = p.doc_id + sh.t_start[t];
-        const float* __restrict__ imp = p.impact + sh.t_start[t];
-        const float mult = sh.t_mult[t];
-        const int sl0 = int(slab0 - 0);  // slab0 < 2^31 (doc ids are int32)
-        for (int i = lo + tid; i < hi; i += BM25_THREADS * BM25_UNROLL) {
-          int d[BM25_UNROLL]; float v[BM25_UNROLL];
-#pragma unroll
-          for (int u = 0; u < BM25_UNROLL; ++u) {
-            const int ii = i + u * BM25_THREADS;
-            const bool ok = ii < hi;
-            d[u] = ok ? __ldcs(ids + ii) - sl0 : -1;
-            v[u] = ok ? __ldcs(imp + ii) : 0.f;
-          }
-          float a[BM25_UNROLL];
-#pragma unroll
-          for (int u = 0; u < BM25_UNROLL; ++u) a[u] = (d[u] >= 0) ? acc[d[u]] : 0.f;
-#pragma unroll
-          for (int u = 0; u < BM25_UNROLL; ++u) if (d[u] >= 0) acc[d[u]] = fmaf(mult, v[u], a[u]);
-        }
-        __syncthreads();
-      }
-      // ---- 3. scan the slab for candidates ----
+      // ---- 3. scan the slab for candidates (fast path: nothing in this thread's 32 docs beats thr) ----
       const int cnt_before = sh.cand_cnt;
       const unsigned long long thr_key = sh.thr_key;
-      const float thr_s = thr_key ? key_score(thr_key) : -INFINITY;
+      // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
+      const float thr_s = !thr_key ? -INFINITY : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
       __syncthreads();   // everyone has read cand_cnt before anyone appends
       {
         const float4* a4 = reinterpret_cast<const float4*>(acc);
-#pragma unroll 2
-        for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) {
-          const int idx = (tid + i * BM25_THREADS) * 4;
-          const float4 s4 = a4[tid + i * BM25_THREADS];
-          const float s[4] = {s4.x, s4.y, s4.z, s4.w};
+        float4 s4[BM25_SLAB / 4 / BM25_THREADS];
+        float mx = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int64_t doc = slab0 + idx + e;
-            bool want = (s[e] >= thr_s) && (doc < range_end);
-            uint64_t key = 0;
-            if (want) { key = make_key(s[e], uint32_t(doc)); want = key > thr_key; }
-            cand_append(want, key, cand, cap, &sh.cand_cnt);
+        for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) {
+          s4[i] = a4[tid + i * BM25_THREADS];
+          mx = fmaxf(mx, fmaxf(fmaxf(s4[i].x, s4[i].y), fmaxf(s4[i].z, s4[i].w)));
+        }
+        if (__any_sync(0xffffffffu, mx >= thr_s)) {
+#pragma unroll
+          for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) {
+            const int idx = (tid + i * BM25_THREADS) * 4;
+            const float sv[4] = {s4[i].x, s4[i].y, s4[i].z, s4[i].w};
+            const bool any4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3])) >= thr_s;
+            if (!__any_sync(0xffffffffu, any4)) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int64_t doc = slab0 + idx + e;
+              bool want = (sv[e] >= thr_s) && (doc < range_end);
+              uint64_t key = 0;
+              if (want) { key = make_key(sv[e], uint32_t(doc)); want = key > thr_key; }
+              cand_append(want, key, cand, cap, &sh.cand_cnt);
+            }
           }
         }
       }
@@ -257,6 +308,13 @@ bm25_scan_kernel(const Bm25Params p) {
         if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
         __syncthreads();
       }
+      // ---- re-zero the slab for the next one ----
+      {
+        float4* a4 = reinterpret_cast<float4*>(acc);
+#pragma unroll
+        for (int i = 0; i < BM25_SLAB / 4 / BM25_THREADS; ++i) a4[tid + i * BM25_THREADS] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
     }
   }
 

@@ -351,3 +351,24 @@ def test_fuse_batch_matches_oracle_and_filters(eng):
                 if near:
                     continue
                 check_topk_parity(s[q:q + 1], i[q:q + 1], O_s, O_i, 100, TAU_FP32, what=f"fuse-batch-{method}")
+
+
+def test_bm25_device_built_scale_model_matches_oracle(eng):
+    """SURVEY 8d config 4's 50 000-doc / 5 000-term scale model, index built on the device by the bench's
+    generator, scored by the kernel, checked against the fp64 oracle on the same postings."""
+    from legal_rag_b200 import synth
+    index, st = synth.bm25_synthetic_index(50_000, 5_000, 10, "cuda", chunk_docs=16_000, keep_tf=True)
+    csr = obm25.CsrBM25(index.indptr.cpu().numpy(), index.doc_id.cpu().numpy().astype(np.int64), st["tf"].cpu().numpy().astype(np.int64),
+                        st["doc_len"].cpu().numpy())
+    assert csr.avgdl == pytest.approx(st["avgdl"])
+    # the device builder's impacts are the oracle's per-posting contributions
+    t_of = np.repeat(np.arange(5_000), np.diff(csr.indptr))
+    f = csr.tf.astype(np.float64)
+    imp = csr.idf[t_of] * (f * 2.5 / (f + 1.5 * (0.25 + 0.75 * csr.doc_len[csr.doc_id] / csr.avgdl)))
+    np.testing.assert_allclose(index.impact.cpu().numpy(), imp, rtol=2e-7)
+    qi, qt, mx = synth.bm25_synthetic_queries(256, 5_000, 11, "cuda")
+    s, i = eng.bm25_topk(index, qi, qt, mx, 100)
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    qi, qt = qi.cpu().numpy(), qt.cpu().numpy()
+    O = [csr.search(qt[qi[j]:qi[j + 1]].tolist(), 150) for j in range(256)]
+    check_topk_parity(s, i, np.stack([o[0] for o in O]), np.stack([o[1] for o in O]), 100, TAU_FP32, what="bm25-scale-model")

@@ -8,6 +8,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py "$@" --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list exit $?"
 python bench.py "$@" --no-cpu-baseline > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s 3 -c 1 -f -o gpurun_out/prof_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:$KREGEX -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-1} -f -o gpurun_out/prof_$TAG \
     python bench.py "$@" --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full capture exit $?"
