@@ -258,21 +258,23 @@ def shard_range(n_total: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n_total, lo + per)
 
 
-def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None):
+def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None, merge=None):
     """The one exchange step of the sharded path: all-gather each rank's local top-k (global ids) over
-    NCCL (gloo on CPU tensors in tests) and k-way merge, replicated on every rank."""
+    NCCL and k-way merge, replicated on every rank.  `merge` defaults to the liblrag merge kernel; the CPU
+    gloo tests of this plumbing pass the oracle's merge instead."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return scores, ids
     world = dist.get_world_size(group)
     nq = scores.shape[0]
-    gs = torch.empty((world, nq, k), dtype=scores.dtype, device=scores.device)
-    gi = torch.empty((world, nq, k), dtype=ids.dtype, device=ids.device)
+    gs = torch.empty((world * nq, k), dtype=scores.dtype, device=scores.device)
+    gi = torch.empty((world * nq, k), dtype=ids.dtype, device=ids.device)
     dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
+    gs, gi = gs.view(world, nq, k), gi.view(world, nq, k)
     cat_s = gs.permute(1, 0, 2).reshape(nq, world * k).contiguous()
     cat_i = gi.permute(1, 0, 2).reshape(nq, world * k).contiguous()
-    return topk_merge(cat_s, cat_i, k)
+    return (merge or topk_merge)(cat_s, cat_i, k)
 
 
 class FlatIPShard:

@@ -1,0 +1,72 @@
+"""BM25Retriever (replaces legalrag/retrieval/bm25_retriever.py:17-76): bm25.pkl is unpickled (with a shim
+when rank_bm25 is not installed), converted once to device-resident CSR postings, and every search is the
+liblrag BM25 kernel -- scoring and the full ranking the reference does in Python."""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from .. import engine
+from ..bm25_index import Bm25HostIndex
+from ..schemas import LawChunk, chunk_from_obj
+from . import artifacts, encoders
+
+
+class BM25Retriever:
+    def __init__(self, cfg, tokenizer: Optional[Callable[[str], List[str]]] = None):
+        self.cfg = cfg
+        self.bm25_path = Path(cfg.retrieval.bm25_index_file)
+        self.device = torch.device(getattr(cfg, "device", None) or "cuda")
+        self.tokenizer = tokenizer or encoders.default_query_tokenizer()
+        self._loaded = False
+        self._bm25_mtime: Optional[float] = None
+        self.bm25 = None                          # the unpickled BM25Okapi (or its stand-in)
+        self.chunks: List[LawChunk] = []
+        self.host_index: Optional[Bm25HostIndex] = None
+        self.device_index: Optional[engine.Bm25DeviceIndex] = None
+
+    def load(self) -> None:
+        if not self.bm25_path.exists():
+            raise RuntimeError(f"[BM25] index not found: {self.bm25_path}. "
+                               f"Run: python build_index.py (or python build_index.py --only-bm25)")
+        current_mtime = self.bm25_path.stat().st_mtime
+        if self._loaded and self._bm25_mtime == current_mtime:
+            return
+        obj = artifacts.read_bm25_pickle(self.bm25_path)
+        bm25 = obj.get("bm25")
+        if bm25 is None:
+            raise RuntimeError(f"[BM25] invalid index file (missing 'bm25'): {self.bm25_path}")
+        try:
+            chunks = [chunk_from_obj(c) for c in obj.get("chunks", [])]
+        except RuntimeError as e:
+            raise RuntimeError(f"[BM25] {e}") from e
+        host = Bm25HostIndex.from_okapi(bm25)
+        dev = host.to_device(self.device)
+        # publish the finished snapshot in one step
+        self.bm25, self.chunks, self.host_index, self.device_index = bm25, chunks, host, dev
+        self._loaded, self._bm25_mtime = True, current_mtime
+
+    def search_ids(self, token_lists: Sequence[Sequence[str]], top_k: int):
+        """Pre-tokenised queries -> (scores [nq, k], doc rows [nq, k]) on the device."""
+        self.load()
+        host, dev = self.host_index, self.device_index
+        k = max(1, min(int(top_k), engine.LRAG_MAX_K))
+        token_lists = [list(t)[: engine.LRAG_BM25_MAX_QUERY_TERMS] for t in token_lists]
+        qi, qt, mx = host.encode_queries(token_lists)
+        return engine.bm25_topk(dev, torch.from_numpy(qi).to(self.device), torch.from_numpy(qt).to(self.device), mx, k)
+
+    def search(self, query: str, top_k: int) -> List[Tuple[LawChunk, float]]:
+        self.load()
+        n = len(self.chunks)
+        s, i = self.search_ids([self.tokenizer(query)], top_k)
+        s, i = s[0].tolist(), i[0].tolist()
+        return [(self.chunks[d], float(sc)) for sc, d in zip(s, i) if 0 <= d < n][: int(top_k)]
+
+    def search_batch(self, queries: Sequence[str], top_k: int) -> List[List[Tuple[LawChunk, float]]]:
+        self.load()
+        n = len(self.chunks)
+        s, i = self.search_ids([self.tokenizer(q) for q in queries], top_k)
+        s, i = s.tolist(), i.tolist()
+        return [[(self.chunks[d], float(sc)) for sc, d in zip(rs, ri) if 0 <= d < n] for rs, ri in zip(s, i)]

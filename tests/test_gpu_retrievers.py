@@ -1,0 +1,160 @@
+"""GPU tests of the reference-shaped classes: artifacts are written by this package's builders with
+deterministic stand-in encoders, searched through DenseRetriever / BM25Retriever / ColBERTRetriever /
+HybridRetriever exactly as RagPipeline would, and every stage is compared with the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import bm25 as obm25
+from oracle import dense as odense
+from oracle import fuse as ofuse
+from oracle import maxsim as omaxsim
+from tests.parity import check_topk_parity
+
+pytestmark = pytest.mark.gpu
+
+QUESTIONS = [
+    "What remedies does a buyer have when the seller fails to deliver conforming goods?",
+    "perfection of a security interest in deposit accounts",
+    "negotiable instrument holder in due course",
+    "Letter of credit issuer obligations and the independence principle",
+    "warranty of merchantability disclaimer",
+]
+
+
+@pytest.fixture(scope="module")
+def world(golden_dir, tmp_path_factory):
+    from legal_rag_b200.config import AppConfig
+    from legal_rag_b200.retrieval import builders, encoders
+    from legal_rag_b200.schemas import LawChunk
+    z = np.load(os.path.join(golden_dir, "ucc_corpus.npz"))
+    lens, flat, vocab, ids = z["doc_len"], z["tokens"].astype(np.int64), z["vocab"], z["ids"]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    texts = [" ".join(vocab[flat[off[i]:off[i + 1]]]) for i in range(len(lens))]
+    chunks = [LawChunk(id=str(ids[i]), law_name="UCC", article_no=str(i), article_id=str(i), text=texts[i], lang="en")
+              for i in range(len(texts))]
+    root = tmp_path_factory.mktemp("index")
+    cfg = AppConfig()
+    r = cfg.retrieval
+    r.faiss_index_file, r.faiss_meta_file = str(root / "faiss" / "faiss.index"), str(root / "faiss" / "faiss_meta.jsonl")
+    r.bm25_index_file = str(root / "bm25.pkl")
+    r.colbert_index_path, r.colbert_meta_file = str(root / "colbert"), str(root / "colbert" / "colbert_meta.jsonl")
+    r.colbert_doc_maxlen = 96
+    dense_enc, tok_enc = encoders.HashingDenseEncoder(768), encoders.HashingTokenEncoder(doc_maxlen=96)
+    encoders.register_dense_encoder(lambda name, dev: dense_enc)
+    encoders.register_token_encoder(lambda name, dev: tok_enc)
+    builders.build_faiss_index(cfg, chunks, flat=False)          # HNSW container, like the reference writes
+    builders.build_bm25_index(cfg, chunks)
+    builders.build_colbert_index(cfg, chunks)
+    yield {"cfg": cfg, "chunks": chunks, "texts": texts, "dense_enc": dense_enc, "tok_enc": tok_enc, "root": root}
+    encoders.register_dense_encoder(None)
+    encoders.register_token_encoder(None)
+
+
+def _oracle_channels(world, question, k):
+    from legal_rag_b200.retrieval import encoders
+    texts, chunks = world["texts"], world["chunks"]
+    X = world["dense_enc"].encode(texts)
+    q = world["dense_enc"].encode_queries([question])
+    dS, dI = odense.flat_ip_topk(q, X, k)
+    lit = obm25.BM25Okapi([encoders.tokenize_en(t) for t in texts])
+    bS, bI = obm25.search(lit, encoders.default_query_tokenizer()(question), k)
+    D = np.zeros((len(texts), 96, 128), np.float32); dl = np.zeros(len(texts), np.int64)
+    for i, t in enumerate(texts):
+        m = world["tok_enc"].encode_doc(t)
+        D[i, :len(m)] = m; dl[i] = len(m)
+    Qm = world["tok_enc"].encode_query(question)[None]
+    cS, cI = omaxsim.rerank_topk(Qm, D, dl, np.arange(len(texts))[None], k)
+    return (dS[0], dI[0]), (bS, bI), (cS[0], cI[0])
+
+
+def test_channels_match_oracle_through_the_retriever_classes(world):
+    from legal_rag_b200.retrieval import HybridRetriever
+    hr = HybridRetriever(world["cfg"])
+    assert hr.colbert is not None and hr.graph is None
+    row = {c.id: i for i, c in enumerate(world["chunks"])}
+    k = 100
+    for qn in QUESTIONS[:3]:
+        (dS, dI), (bS, bI), (cS, cI) = _oracle_channels(world, qn, k + 20)
+        hits = hr.search_dense(qn, k)
+        assert [h.rank for h in hits] == list(range(1, k + 1)) and hits[0].score_breakdown["channel"] == ["dense"]
+        assert hits[0].semantic_score == hits[0].score and hits[0].source == "retriever"
+        check_topk_parity(np.array([[h.score for h in hits]]), np.array([[row[h.chunk.id] for h in hits]]), dS[None], dI[None], k,
+                          1e-2, what="cls-dense", floor=0.1)
+        hits = hr.search_bm25(qn, k)
+        assert len(hits) == k                                   # zero-score documents are returned too
+        check_topk_parity(np.array([[h.score for h in hits]]), np.array([[row[h.chunk.id] for h in hits]]), bS[None], bI[None], k,
+                          1e-3, what="cls-bm25")
+        hits = hr.search_colbert(qn, k)
+        check_topk_parity(np.array([[h.score for h in hits]]), np.array([[row[h.chunk.id] for h in hits]]), cS[None], cI[None], k,
+                          1e-2, what="cls-colbert", floor=1.0)
+        assert hits[0].score_breakdown["channel"] == ["colbert"] and "colbert_raw" in hits[0].score_breakdown
+
+
+@pytest.mark.parametrize("method", ["rrf_norm_blend", "weighted_sum", "rrf", "wrrf"])
+def test_fuse_and_search_match_oracle(world, method):
+    from legal_rag_b200.retrieval import HybridRetriever
+    cfg = world["cfg"]
+    cfg.retrieval.fusion_method = method
+    cfg.retrieval.top_k = 100
+    hr = HybridRetriever(cfg)
+    row = {c.id: i for i, c in enumerate(world["chunks"])}
+    qn = QUESTIONS[0]
+    d, b, c = hr.search_dense(qn, 100), hr.search_bm25(qn, 100), hr.search_colbert(qn, 100)
+    # _fuse breaks exact score ties by first appearance (dense, bm25, colbert lists); number the chunks that way
+    row = {}
+    for h in d + b + c:
+        row.setdefault(h.chunk.id, len(row))
+    pairs = lambda hs: [(row[h.chunk.id], float(np.float32(h.score))) for h in hs]   # noqa: E731
+    ref = ofuse.fuse(pairs(d), pairs(b), pairs(c), method=method, w_dense=0.6, w_bm25=0.4, w_colbert=0.35, rrf_k=60, alpha=0.5)
+    fused = hr._fuse(dense_hits=d, bm25_hits=b, colbert_hits=c)
+    assert len(fused) == len(ref) and [h.rank for h in fused] == list(range(1, len(ref) + 1))
+    check_topk_parity(np.array([[h.score for h in fused]]), np.array([[row[h.chunk.id] for h in fused]]),
+                      np.array([[r["score"] for r in ref]]), np.array([[r["id"] for r in ref]]), len(ref), 1e-3, what=f"cls-fuse-{method}")
+    by = {r["id"]: r for r in ref}
+    for h in fused[:50]:
+        r, sb = by[row[h.chunk.id]], h.score_breakdown
+        assert sb["fusion_method"] == method and sb["rrf_k"] == 60 and set(sb["channel_contrib"]) == {"dense", "bm25", "colbert"}
+        for key in ("rrf_norm", "weighted_sum", "dense_norm", "bm25_norm", "colbert_norm"):
+            assert sb[key] == pytest.approx(r[key], rel=1e-3, abs=1e-5)
+        for ch in ("dense", "bm25", "colbert"):
+            assert sb["channel_contrib"][ch] == pytest.approx(r["channel_contrib"][ch], rel=1e-3, abs=1e-5)
+    # full search: min_final_score filter (0.2) + slice; positional (question, llm, top_k, decision) order
+    out = hr.search(qn, None, 10, None)
+    want = [r for r in ref if r["score"] >= 0.2][:12]
+    assert 0 < len(out) <= 10 and all(h.score >= 0.2 for h in out)
+    check_topk_parity(np.array([[h.score for h in out]]), np.array([[row[h.chunk.id] for h in out]]),
+                      np.array([[r["score"] for r in want]]), np.array([[r["id"] for r in want]]), len(out), 1e-3, what="cls-search")
+    cfg.retrieval.fusion_method, cfg.retrieval.top_k = "rrf_norm_blend", 10
+
+
+def test_search_batch_equals_per_question_search(world):
+    from legal_rag_b200.retrieval import HybridRetriever
+    cfg = world["cfg"]
+    hr = HybridRetriever(cfg)
+    row = {c.id: i for i, c in enumerate(world["chunks"])}
+    batch = hr.search_batch(QUESTIONS, top_k=10)
+    for qn, got in zip(QUESTIONS, batch):
+        one = hr.search(qn, None, 10)
+        check_topk_parity(np.array([[h.score for h in got]]), np.array([[row[h.chunk.id] for h in got]]),
+                          np.array([[h.score for h in one]]), np.array([[row[h.chunk.id] for h in one]]), len(one), 1e-3, what="cls-batch")
+
+
+def test_incremental_add_is_searchable_and_persisted(world):
+    from legal_rag_b200.retrieval import VectorStore, artifacts, builders
+    from legal_rag_b200.schemas import LawChunk
+    cfg = world["cfg"]
+    store = VectorStore.from_config(cfg)
+    store.load()
+    n0 = store.index.ntotal
+    new = LawChunk(id="new::1", law_name="UCC", article_no="x", article_id="x", lang="en",
+                   text="zebra quagga okapi unmistakable marker sentence about striped equids")
+    assert builders.IncrementalDenseBuilder(cfg, store).add_chunks([new]) == 1
+    assert store.index.ntotal == n0 + 1 and len(store.chunks) == n0 + 1
+    hits = store.search("zebra quagga okapi striped equids", 3)
+    assert hits[0][0].id == "new::1"
+    X, info = artifacts.read_faiss_index(cfg.retrieval.faiss_index_file)      # rewritten as a flat file, row count grown
+    assert X.shape[0] == n0 + 1 and len(artifacts.read_meta_jsonl(cfg.retrieval.faiss_meta_file)) == n0 + 1

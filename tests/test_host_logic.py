@@ -1,0 +1,161 @@
+"""CPU tests of the host side: artifact formats, BM25 index construction, tokenisation, shard maths,
+the dedup rule, and the multi-rank gather/merge plumbing on gloo."""
+import json
+import os
+import pickle
+import struct
+
+import numpy as np
+import pytest
+
+from legal_rag_b200.bm25_index import Bm25HostIndex
+from legal_rag_b200.retrieval import artifacts, encoders
+from legal_rag_b200.schemas import LawChunk, RetrievalHit
+from oracle import bm25 as obm25
+
+
+def _chunks(n, lang="en"):
+    return [LawChunk(id=f"c{i}", law_name="UCC", article_no=str(i), article_id=str(i), text=f"text number {i}", lang=lang)
+            for i in range(n)]
+
+
+# ---------------------------------------------------------------- faiss files
+def test_faiss_flat_roundtrip_and_handmade_header(tmp_path):
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((37, 24)).astype(np.float32)
+    p = tmp_path / "faiss.index"
+    artifacts.write_faiss_flat(p, X)
+    raw = p.read_bytes()
+    assert raw[:4] == b"IxFI" and len(raw) == 45 + 37 * 24 * 4           # 45-byte header
+    d, n = struct.unpack_from("<iq", raw, 4)
+    assert (d, n) == (24, 37) and struct.unpack_from("<Q", raw, 37)[0] == 37 * 24
+    Y, info = artifacts.read_faiss_index(p)
+    np.testing.assert_array_equal(X, Y)
+    assert info["metric"] == artifacts.METRIC_INNER_PRODUCT and info["hnsw"] is None
+    # a byte string assembled by hand, L2 metric
+    blob = b"IxF2" + struct.pack("<iqqqBi", 2, 3, 0, 0, 1, 1) + struct.pack("<Q", 6) + np.arange(6, dtype=np.float32).tobytes()
+    (tmp_path / "h.index").write_bytes(blob)
+    Y, info = artifacts.read_faiss_index(tmp_path / "h.index")
+    assert Y.tolist() == [[0, 1], [2, 3], [4, 5]] and info["metric"] == artifacts.METRIC_L2
+
+
+def test_faiss_hnsw_container_is_unwrapped(tmp_path):
+    X = np.random.default_rng(1).standard_normal((11, 8)).astype(np.float32)
+    p = tmp_path / "hnsw.index"
+    artifacts.write_faiss_hnsw_flat(p, X)
+    Y, info = artifacts.read_faiss_index(p)
+    np.testing.assert_array_equal(X, Y)
+    assert info["outer_fourcc"] == "IHNf" and info["fourcc"] == "IxFI"
+    # unknown bytes between the graph and the storage: the reader locates the nested flat index
+    raw = p.read_bytes()
+    pos = raw.index(b"IxFI", 4)
+    (tmp_path / "odd.index").write_bytes(raw[:pos] + b"\x07" * 12 + raw[pos:])
+    Y, _ = artifacts.read_faiss_index(tmp_path / "odd.index")
+    np.testing.assert_array_equal(X, Y)
+    with pytest.raises(ValueError, match="unsupported index type"):
+        (tmp_path / "ivf.index").write_bytes(b"IwFl" + b"\0" * 64)
+        artifacts.read_faiss_index(tmp_path / "ivf.index")
+
+
+def test_meta_jsonl_roundtrip(tmp_path):
+    cs = _chunks(5)
+    artifacts.write_meta_jsonl(tmp_path / "m.jsonl", cs)
+    assert [c.id for c in artifacts.read_meta_jsonl(tmp_path / "m.jsonl")] == [c.id for c in cs]
+    artifacts.write_colbert_meta(tmp_path / "c.jsonl", cs)
+    back = artifacts.read_colbert_meta(tmp_path / "c.jsonl")
+    assert sorted(back) == list(range(5)) and back[3].id == "c3"
+
+
+# ---------------------------------------------------------------- bm25.pkl
+CORPUS = [["a", "b", "b", "c"], ["a", "c"], ["a", "d", "d", "d"], ["e", "b"], ["f"]]
+
+
+def test_okapi_state_matches_the_oracle_transcription():
+    st = artifacts.okapi_state_from_tokens(CORPUS)
+    lit = obm25.BM25Okapi(CORPUS)
+    assert st.idf == lit.idf and st.avgdl == lit.avgdl and st.doc_len == lit.doc_len
+    assert st.doc_freqs == lit.doc_freqs and st.average_idf == lit.average_idf and st.corpus_size == 5
+
+
+def test_bm25_pickle_is_written_by_reference_and_read_with_the_shim(tmp_path):
+    st = artifacts.okapi_state_from_tokens(CORPUS)
+    p = tmp_path / "bm25.pkl"
+    artifacts.write_bm25_pickle(p, st, _chunks(5))
+    raw = p.read_bytes()
+    assert b"rank_bm25" in raw and b"BM25Okapi" in raw       # what pickle.load resolves in the reference
+    with pytest.raises((ModuleNotFoundError, ImportError, AttributeError)):
+        pickle.loads(raw)                                     # the library is not installed here ...
+    obj = artifacts.read_bm25_pickle(p)                       # ... the shim reader does not need it
+    assert set(obj) == {"bm25", "chunks"} and isinstance(obj["chunks"][0], dict)
+    assert obj["bm25"].idf == st.idf and obj["bm25"].doc_freqs == st.doc_freqs and obj["bm25"].k1 == 1.5
+
+
+def test_host_index_from_okapi_equals_from_tokens_and_oracle():
+    st = artifacts.okapi_state_from_tokens(CORPUS)
+    a = Bm25HostIndex.from_okapi(st)
+    b = Bm25HostIndex.from_tokens(CORPUS)
+    lit = obm25.BM25Okapi(CORPUS)
+    for w, i in a.term_to_id.items():
+        j = b.term_to_id[w]
+        assert a.idf[i] == pytest.approx(b.idf[j], rel=1e-12) == pytest.approx(lit.idf[w], rel=1e-12)
+        np.testing.assert_array_equal(a.doc_id[a.indptr[i]:a.indptr[i + 1]], b.doc_id[b.indptr[j]:b.indptr[j + 1]])
+    # per-posting impacts sum to get_scores
+    imp = a.impacts()
+    for q in (["a"], ["b", "b", "zzz", "a"], ["d", "f"]):
+        sc = np.zeros(5)
+        for w in q:
+            i = a.term_to_id.get(w)
+            if i is not None:
+                sl = slice(a.indptr[i], a.indptr[i + 1])
+                np.add.at(sc, a.doc_id[sl], imp[sl].astype(np.float64))
+        np.testing.assert_allclose(sc, lit.get_scores(q), rtol=1e-6, atol=1e-7)
+    qi, qt, mx = a.encode_queries([["a", "zzz", "a"], [], ["f"]])
+    assert qi.tolist() == [0, 3, 3, 4] and qt.tolist() == [a.term_to_id["a"], -1, a.term_to_id["a"], a.term_to_id["f"]] and mx == 3
+
+
+def test_query_tokenizer_keeps_case_and_whitespace_tokens():
+    tok = encoders.default_query_tokenizer()
+    out = tok("Buyer's remedies, Article 2")
+    assert "Buyer's" in out or "Buyer" in out          # jieba (if present) may split the apostrophe
+    assert any(t.isspace() for t in out)               # whitespace tokens never match the index
+    assert encoders.tokenize_en("Buyer's remedies, Article 2") == ["buyer's", "remedies", "article", "2"]
+
+
+# ---------------------------------------------------------------- hybrid host logic
+def test_dedup_keep_best_matches_reference_golden(golden_dir):
+    from legal_rag_b200.retrieval.hybrid_retriever import _dedup_keep_best
+    with open(os.path.join(golden_dir, "fuse_golden.json")) as f:
+        want = json.load(f)["helpers"]["dedup_E8"]
+    c1, c2 = [LawChunk(id=f"d{i}", law_name="L", article_no=str(i), article_id=str(i), text="t") for i in (1, 2)]
+    hs = [RetrievalHit(chunk=c1, score=0.4, score_breakdown={"channel": ["dense"], "channel_contrib": {"dense": .4}}),
+          RetrievalHit(chunk=c1, score=0.7, source="graph", score_breakdown={"channel": "graph"}),
+          RetrievalHit(chunk=c2, score=0.5, score_breakdown={"channel": ["bm25"]})]
+    got = _dedup_keep_best(hs)
+    assert [(h.chunk.id, h.score, h.rank, h.source) for h in got] == [(w["id"], w["score"], w["rank"], w["source"]) for w in want]
+    assert sorted(got[0].score_breakdown["channel"]) == want[0]["channel"]
+    assert got[0].score_breakdown["channel_contrib"] == want[0]["channel_contrib"]
+
+
+def test_error_contracts_without_touching_the_gpu(tmp_path):
+    from legal_rag_b200.config import AppConfig
+    from legal_rag_b200.retrieval import BM25Retriever, VectorStore
+    cfg = AppConfig()
+    cfg.retrieval.faiss_index_file = str(tmp_path / "nope.index")
+    cfg.retrieval.faiss_meta_file = str(tmp_path / "nope.jsonl")
+    cfg.retrieval.bm25_index_file = str(tmp_path / "nope.pkl")
+    with pytest.raises(FileNotFoundError):                    # tests/test_retrieval.py:114-122 of the reference
+        VectorStore(cfg).load()
+    with pytest.raises(RuntimeError, match="index not found"):
+        BM25Retriever(cfg).load()
+    with open(tmp_path / "nope.pkl", "wb") as f:
+        pickle.dump({"chunks": []}, f)
+    with pytest.raises(RuntimeError, match="missing 'bm25'"):
+        BM25Retriever(cfg).load()
+
+
+def test_shard_ranges_cover_the_corpus():
+    from legal_rag_b200.engine import shard_range
+    for n, w in [(100, 8), (7, 8), (10_000_000, 3), (0, 2)]:
+        spans = [shard_range(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

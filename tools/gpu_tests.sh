@@ -14,3 +14,6 @@ run bm25 "bm25"
 run dense_ref "dense_cuda_core"
 run maxsim "maxsim"
 run dense "dense_tcgen05 or dense_duplicate or dense_rejects"
+echo "=== retrievers" | tee -a gpurun_out/tests.log
+timeout 900 python -m pytest tests/test_gpu_retrievers.py -m gpu -x -q > gpurun_out/test_retrievers.log 2>&1
+echo "exit $? : $(tail -1 gpurun_out/test_retrievers.log)" | tee -a gpurun_out/tests.log
