@@ -105,7 +105,7 @@ int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
  * BM25 channel.  Replaces `bm25.get_scores(tokens)` + the full Python sort at
  * legalrag/retrieval/bm25_retriever.py:74-75 (rank_bm25.BM25Okapi).
  * Index = term-major CSR with doc ids ascending inside each term:
- *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard), impact [nnz] fp32
+ *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard, 16-byte aligned), impact [nnz] fp32
  *   = idf[t] * tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))  with GLOBAL idf/avgdl.
  * Queries = CSR of term ids: q_indptr [nq+1] int64, q_term [*] int32 (repeats allowed and
  * scored once per occurrence, -1 / out-of-range = OOV).
@@ -117,7 +117,7 @@ int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
  * documents are filled in by id; with nonneg == 0 every document of every slab is ranked. */
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
 int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,
-                   const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                   int64_t nnz, const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                    int64_t N, int k, int64_t id_base, int nonneg, float* out_score, int64_t* out_id,
                    void* ws, size_t ws_bytes, lrag_stream_t stream);
 

@@ -9,6 +9,18 @@ namespace lrag {
 
 constexpr int SELECT_THREADS = 256;
 
+// Barrier over the threads that take part in a block-level primitive: the whole CTA by default, or a
+// named barrier over the first `n` threads when other warps of the CTA are busy elsewhere.
+struct CtaBarrier {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+  __device__ __forceinline__ int threads() const { return blockDim.x; }
+};
+struct NamedBarrier {
+  int id, n;
+  __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+  __device__ __forceinline__ int threads() const { return n; }
+};
+
 struct SelectShared {
   int hist[256];
   unsigned long long prefix;
@@ -20,21 +32,21 @@ struct SelectShared {
 // Finds the pivot such that exactly k candidate keys are >= pivot (all of them when there are fewer
 // than k).  ForEach: `template <class F> __device__ void operator()(F&& f) const` calls f(key) for
 // every candidate this thread owns.  Every thread of the block (>= 256 threads) must call.
-template <class ForEach>
-__device__ unsigned long long block_select_pivot(const ForEach& for_each, int k, SelectShared& sm) {
+template <class ForEach, class Bar = CtaBarrier>
+__device__ unsigned long long block_select_pivot(const ForEach& for_each, int k, SelectShared& sm, Bar bar = Bar()) {
   const int tid = threadIdx.x;
-  __syncthreads();
+  bar();
   if (tid == 0) { sm.prefix = 0; sm.mask = 0; sm.remaining = k; sm.nsel = 0; }
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
     if (tid < 256) sm.hist[tid] = 0;
-    __syncthreads();
+    bar();
     if (sm.remaining <= 0) break;
     const unsigned long long prefix = sm.prefix, mask = sm.mask;
     for_each([&](uint64_t key) {
       if ((key & mask) == prefix) atomicAdd(&sm.hist[(key >> shift) & 255], 1);
     });
-    __syncthreads();
+    bar();
     if (tid < 32) {
       // lane l owns bins [8l, 8l+8); find the bin holding the `remaining`-th largest key
       int c[8], local = 0;
@@ -66,26 +78,28 @@ __device__ unsigned long long block_select_pivot(const ForEach& for_each, int k,
         }
       }
     }
-    __syncthreads();
+    bar();
   }
   const unsigned long long pivot = (sm.remaining < 0) ? 0ull : sm.prefix;
-  __syncthreads();
+  bar();
   return pivot;
 }
 
 // Bitonic sort of P (power of two) keys in shared memory, largest first.
-__device__ __forceinline__ void block_sort_desc(uint64_t* key, int P) {
+template <class Bar = CtaBarrier>
+__device__ __forceinline__ void block_sort_desc(uint64_t* key, int P, Bar bar = Bar()) {
   const int tid = threadIdx.x;
+  const int nthr = bar.threads();
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < P / 2; i += blockDim.x) {
+      for (int i = tid; i < P / 2; i += nthr) {
         const int lo = 2 * i - (i & (stride - 1));
         const int hi = lo + stride;
         const bool desc = ((lo & size) == 0);
         const uint64_t a = key[lo], b = key[hi];
         if (desc ? (a < b) : (a > b)) { key[lo] = b; key[hi] = a; }
       }
-      __syncthreads();
+      bar();
     }
   }
 }

@@ -136,7 +136,7 @@ def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tens
         raise LragError(f"a query has {max_query_terms} tokens; at most {LRAG_BM25_MAX_QUERY_TERMS} are supported")
     s, i = _out(nq, k, dev)
     ws = _ws(lib.lrag_bm25_topk_workspace_bytes(index.n_docs, nq, k, max_query_terms), dev)
-    rc = lib.lrag_bm25_topk(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, _ptr(q_indptr),
+    rc = lib.lrag_bm25_topk(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, index.nnz, _ptr(q_indptr),
                             _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
                             _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
     check(rc, "lrag_bm25_topk")
