@@ -116,6 +116,11 @@ int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
  * average idf is positive): doc slabs no query term touches are then skipped and zero-score
  * documents are filled in by id; with nonneg == 0 every document of every slab is ranked. */
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
+/* Tuning knob (process-wide; call before sizing the workspace): documents per work item =
+ * slabs * 16384.  Small items keep the posting ranges all queries are working on inside L2;
+ * large items amortise the per-item state hand-off.  0 restores the default (8, or the
+ * LRAG_BM25_ITEM_SLABS environment variable). */
+int lrag_bm25_set_item_slabs(int slabs);
 int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,
                    int64_t nnz, const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                    int64_t N, int k, int64_t id_base, int nonneg, float* out_score, int64_t* out_id,

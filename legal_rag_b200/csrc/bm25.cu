@@ -2,13 +2,23 @@
 // `bm25.get_scores(tokens)` and the full Python sort at legalrag/retrieval/bm25_retriever.py:74-75
 // of the reference; rank_bm25.BM25Okapi semantics, see oracle/bm25.py).
 //
-// HBM-bound integer/float streaming work, no tensor cores.  One CTA owns one (query, doc-range)
-// pair and walks its range slab by slab (BM25_SLAB docs = 64 KB of fp32 accumulators in shared
-// memory).  The CTA is warp-specialised so that posting traffic never waits for the arithmetic and
-// the arithmetic never does bookkeeping:
-//   * bounds warp   -- for the next group of slabs, finds the posting boundaries of every query term
-//                      with one parallel round of windowed binary searches (postings are doc-id
-//                      sorted); double-buffered, one group ahead of the copy warp;
+// HBM/L2-bound integer/float streaming work, no tensor cores.
+//
+// Work decomposition.  A *chain* is one (query, doc split) pair; it walks its split in *items* of
+// `item_slabs` slabs (BM25_SLAB docs = 64 KB of fp32 accumulators in shared memory).  Items are
+// numbered step-major -- item = step * n_chains + chain -- and handed out by an atomic counter to
+// persistent CTAs, so at any moment the whole machine works on the same narrow doc range of every
+// query: a posting list is fetched from HBM once per range and then served from L2 to all the other
+// queries that share the term.  A chain's state between two of its items (term cursors, running
+// threshold, surviving candidates) lives in the workspace; item (step, chain) waits on a flag that
+// item (step - 1, chain) -- always a lower item number, so already claimed by a running CTA -- sets.
+//
+// The CTA is warp-specialised so that posting traffic never waits for the arithmetic and the
+// arithmetic never does bookkeeping:
+//   * bounds warp   -- claims the next item, loads the chain's term cursors and finds the posting
+//                      boundaries of every query term at every slab edge with one parallel round of
+//                      windowed binary searches (postings are doc-id sorted); double-buffered, one
+//                      group of slabs ahead of the copy warp;
 //   * copy warp     -- walks the (slab, term) runs in order and streams them, <= BM25_CHUNK postings at
 //                      a time, into a shared-memory ring with bulk async copies (cp.async.bulk, 16-byte
 //                      aligned source windows) that complete on mbarriers.  Each ring stage carries a
@@ -21,9 +31,14 @@
 //                      a score that reaches the query's running k-th best: only then is the slab
 //                      scanned for candidates (appended to a shared buffer; an overflow triggers an
 //                      exact radix select that raises the threshold).  The slab is re-zeroed.
+//                      ITEM_BEGIN / ITEM_END stages load / store the chain's candidate state; the
+//                      chain's last item sorts its top-k into the per-chain key list.
 // Slabs in which no query term has a posting are skipped when impacts are known non-negative;
 // documents that match nothing (score 0) are then added by the merge step, lowest id first, exactly
-// as the reference's stable sort does.  bm25_merge_kernel merges the per-range lists.
+// as the reference's stable sort does.  bm25_merge_kernel merges the per-split lists of a query.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "select.cuh"
 
@@ -34,36 +49,58 @@ constexpr int BM25_THREADS = BM25_CONSUMERS + 64;    // + copy warp (16) + bound
 constexpr int BM25_SLAB = 16384;
 constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (fewer when a query has many terms)
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
-constexpr int BM25_MAXT = 128;
+constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
 constexpr int BM25_CHUNK = 1024;                     // postings per ring stage
-constexpr int BM25_STAGES = 3;                      // 64 KB slab + 24 KB ring + 8 KB candidates + state: two CTAs per SM
+constexpr int BM25_STAGES = 3;                       // 64 KB slab + 24 KB ring + 8 KB candidates + state: two CTAs per SM
 constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
-constexpr int BM25_F_TERM_END = 1, BM25_F_SLAB_END = 2, BM25_F_END = 4;
+constexpr int BM25_DEFAULT_ITEM_SLABS = 8;
+enum : int { BM25_F_TERM_END = 1, BM25_F_SLAB_END = 2, BM25_F_ITEM_BEGIN = 4, BM25_F_ITEM_END = 8, BM25_F_FINAL = 16, BM25_F_END = 32 };
+
+struct Bm25Ws {
+  unsigned long long* counter;     // next item
+  int* cur_flag;                   // [nc] steps whose final term cursors are published
+  int* cand_flag;                  // [nc] steps whose candidate state is published
+  int* q_nt;                       // [nq] distinct in-vocabulary terms with postings
+  int64_t* tq_start;               // [nq, TS] first posting
+  int32_t* tq_len;                 // [nq, TS] df
+  float* tq_mult;                  // [nq, TS] occurrences in the query
+  int32_t* ch_cur;                 // [nc, TS] postings consumed so far (relative to tq_start)
+  unsigned long long* ch_thr;      // [nc]
+  int* ch_cnt;                     // [nc]
+  uint64_t* ch_cand;               // [nc, cap]
+  uint64_t* out_keys;              // [nc, k] = [nq, S, k]
+};
 
 struct Bm25Params {
   const int64_t* indptr; const int32_t* doc_id; const float* impact; int64_t V; int64_t nnz;
   const int64_t* q_indptr; const int32_t* q_term;
-  int64_t N; int64_t docs_per_split;
-  int nq, k, nonneg, nsplit, cap, P;
-  uint64_t* out_keys;   // [nq, nsplit, k]
+  int64_t N; int64_t dps;          // docs per split (multiple of the item size)
+  unsigned long long total_items;
+  int nq, k, nonneg, S, cap, P, TS, item_slabs, steps, nc;
+  Bm25Ws ws;
+};
+
+struct Bm25Group {                 // bounds warp -> copy warp
+  int kind;                        // 0 = slabs of an item, 1 = no more work
+  int chain, step, first, last, final_step, nt, ns;
+  int b0, range_end;
+  int64_t t_start[BM25_MAXT];
+  float t_mult[BM25_MAXT];
+  int32_t bound[BM25_BOUND_CAP];   // [t * (ns + 1) + j]
+  int32_t any[BM25_MAX_GROUP];
 };
 
 struct Bm25Shared {
   SelectShared sel;
-  int4 sdesc[BM25_STAGES];        // {n, skip | flags << 8, mult (float bits), slab0}
+  int4 sdesc[BM25_STAGES];         // {n, skip | flags << 8, mult (float bits) or step, slab0 or chain}
   uint64_t full_bar[BM25_STAGES], empty_bar[BM25_STAGES];   // posting ring
-  uint64_t bfull_bar[2], bempty_bar[2];                      // bounds buffers
-  int64_t t_start[BM25_MAXT];     // first posting of the term
-  int32_t t_len[BM25_MAXT];       // df
-  int32_t t_cur[BM25_MAXT];       // bounds warp only: postings before the next group (relative)
-  float t_mult[BM25_MAXT];        // occurrences of the term in the query
-  int32_t raw[BM25_MAXT];
-  int32_t owner[BM25_MAXT];
-  int32_t bound[2][BM25_BOUND_CAP];     // [buffer][t * (gs + 1) + j]
-  int32_t slab_any[2][BM25_MAX_GROUP];
-  int nt, gs;
+  uint64_t bfull_bar[2], bempty_bar[2];                      // group buffers
+  Bm25Group grp[2];
+  int64_t t_start[BM25_MAXT];      // bounds warp's view of the current item's query
+  int32_t t_len[BM25_MAXT];
+  int32_t t_cur[BM25_MAXT];
   int cand_cnt;
   unsigned long long thr_key;
 };
@@ -96,6 +133,27 @@ __device__ __forceinline__ bool consumers_bar_or(bool pred) {
       : "r"(uint32_t(pred)), "r"(BM25_BAR_CONSUMERS), "r"(BM25_CONSUMERS)
       : "memory");
   return out != 0;
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded spin on a chain flag: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void spin_until_ge(const int* flag, int want) {
+  if (ld_acquire(flag) >= want) return;
+  const long long t0 = clock64();
+  while (ld_acquire(flag) < want) {
+    __nanosleep(64);
+    if (clock64() - t0 > 20000000000LL) {
+      printf("lrag: bm25 chain flag wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
 }
 
 // warp-aggregated append to the shared candidate buffer (entries past `cap` are dropped and counted)
@@ -133,8 +191,47 @@ struct Bm25Cands {
   }
 };
 
-// One ring stage: postings [pos, pos + n) of term t (t < 0: none) for the slab starting at doc sl0.
-struct Bm25Chunk { int t, pos, n, sl0; };
+// ------------------------------------------------------------------------------------------------
+// Per launch, before the scan: drops OOV terms, merges repeated query terms into a multiplicity
+// (first-occurrence order) and resets the item counter and the chain flags.  One warp per query.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gsz = gridDim.x * blockDim.x;
+  for (int i = gtid; i < p.nc; i += gsz) { p.ws.cur_flag[i] = 0; p.ws.cand_flag[i] = 0; }
+  if (gtid == 0) *p.ws.counter = 0ull;
+  const int lane = threadIdx.x & 31;
+  for (int q = gtid >> 5; q < p.nq; q += gsz >> 5) {
+    const int64_t qs = p.q_indptr[q];
+    const int64_t qlen = p.q_indptr[q + 1] - qs;
+    const int nraw = int(qlen < p.TS ? qlen : p.TS);
+    const int32_t* raw = p.q_term + qs;
+    int base = 0;
+    for (int r0 = 0; r0 < nraw; r0 += 32) {
+      const int i = r0 + lane;
+      int t = -1;
+      if (i < nraw) { t = raw[i]; if (t < 0 || int64_t(t) >= p.V) t = -1; }
+      bool own = t >= 0;
+      for (int j = 0; j < i && own; ++j) own = (raw[j] != t);
+      int64_t s = 0, e = 0;
+      if (own) { s = p.indptr[t]; e = p.indptr[t + 1]; own = e > s; }      // a term without postings scores nothing
+      int mult = 0;
+      if (own) for (int j = i; j < nraw; ++j) mult += (raw[j] == t);
+      const uint32_t m = __ballot_sync(0xffffffffu, own);
+      if (own) {
+        const size_t slot = size_t(q) * p.TS + base + __popc(m & ((1u << lane) - 1));
+        p.ws.tq_start[slot] = s;
+        p.ws.tq_len[slot] = int32_t(e - s);
+        p.ws.tq_mult[slot] = float(mult);
+      }
+      base += __popc(m);
+    }
+    if (lane == 0) p.ws.q_nt[q] = base;
+  }
+}
+
+// One ring stage worth of postings: [first, first + n) of the arrays, for the slab starting at doc sl0.
+struct Bm25Chunk { int64_t first; float mult; int n, sl0, t; };
 
 __global__ void __launch_bounds__(BM25_THREADS, 2)
 bm25_scan_kernel(const Bm25Params p) {
@@ -147,178 +244,200 @@ bm25_scan_kernel(const Bm25Params p) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int q = blockIdx.x / p.nsplit;
-  const int r = blockIdx.x % p.nsplit;
-  const int64_t range_begin = int64_t(r) * p.docs_per_split;
-  const int64_t range_end = min(p.N, range_begin + p.docs_per_split);
   const int cap = p.cap;
+  const unsigned long long thr_init = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull;
 
-  // ---- query terms: drop OOV, merge repeats into a multiplicity (first-occurrence order) ----
-  const int64_t qs = p.q_indptr[q];
-  const int64_t qlen = p.q_indptr[q + 1] - qs;
-  const int nraw = int(qlen < BM25_MAXT ? qlen : BM25_MAXT);
-  if (tid < BM25_MAXT) {
-    int t = -1;
-    if (tid < nraw) { t = p.q_term[qs + tid]; if (t < 0 || int64_t(t) >= p.V) t = -1; }
-    sh.raw[tid] = t;
-  }
   if (tid == 0) {
     sh.cand_cnt = 0;
-    sh.thr_key = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull;
+    sh.thr_key = thr_init;
     for (int s = 0; s < BM25_STAGES; ++s) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], BM25_CONSUMERS / 32); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], 1); }
     fence_barrier_init();
   }
-  __syncthreads();
-  if (tid < BM25_MAXT) {
-    const int t = sh.raw[tid];
-    int own = (t >= 0);
-    for (int j = 0; j < tid && own; ++j) own = (sh.raw[j] != t);
-    if (own && p.indptr[t + 1] == p.indptr[t]) own = 0;   // term without postings
-    sh.owner[tid] = own;
-  }
-  __syncthreads();
-  if (tid < BM25_MAXT && sh.owner[tid]) {
-    const int t = sh.raw[tid];
-    int slot = 0, mult = 0;
-    for (int j = 0; j < tid; ++j) slot += sh.owner[j];
-    for (int j = tid; j < nraw; ++j) mult += (sh.raw[j] == t);
-    const int64_t s = p.indptr[t];
-    sh.t_start[slot] = s;
-    sh.t_len[slot] = int32_t(p.indptr[t + 1] - s);
-    sh.t_mult[slot] = float(mult);
-  }
-  if (tid == 0) {
-    int n = 0;
-    for (int j = 0; j < nraw; ++j) n += sh.owner[j];
-    sh.nt = n;
-    int gs = n > 0 ? BM25_BOUND_CAP / n - 1 : BM25_MAX_GROUP;
-    sh.gs = gs < 1 ? 1 : (gs > BM25_MAX_GROUP ? BM25_MAX_GROUP : gs);
-  }
   // zero the slab once; every slab end leaves it zeroed again
   for (int i = tid; i < BM25_SLAB / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const int nt = sh.nt, gs = sh.gs;
-  const int64_t group_docs = int64_t(BM25_SLAB) * gs;
   const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
 
   if (warp == BM25_CONSUMERS / 32 + 1) {
     // ===================== bounds warp =====================
-    for (int t = lane; t < nt; t += 32)
-      sh.t_cur[t] = range_begin == 0 ? 0 : lower_bound_doc(p.doc_id + sh.t_start[t], 0, sh.t_len[t], range_begin);
-    __syncwarp();
-    uint32_t g = 0;
-    for (int64_t b0 = range_begin; b0 < range_end; b0 += group_docs, ++g) {
-      const uint32_t bb = g & 1;
-      mbar_wait(&sh.bempty_bar[bb], ((g >> 1) & 1) ^ 1);
-      int32_t* bound = sh.bound[bb];
-      for (int w = lane; w < nt * (gs + 1); w += 32) {
-        const int t = w / (gs + 1), j = w % (gs + 1);
-        const int cur = sh.t_cur[t], len = sh.t_len[t];
-        const int64_t target = b0 + int64_t(j) * BM25_SLAB;
-        // ids are strictly increasing inside a term: the answer is at most (target - b0) past cur
-        const int64_t reach = int64_t(cur) + (target - b0);
-        const int hi = int(reach < len ? reach : int64_t(len));
-        bound[w] = (j == 0) ? cur : lower_bound_doc(p.doc_id + sh.t_start[t], cur, hi, target);
+    const int64_t item_docs = int64_t(p.item_slabs) * BM25_SLAB;
+    uint32_t gcount = 0;
+    for (;;) {
+      unsigned long long item = 0;
+      if (lane == 0) item = atomicAdd(p.ws.counter, 1ull);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= p.total_items) break;
+      const int step = int(item / (unsigned long long)p.nc);
+      const int chain = int(item - (unsigned long long)step * p.nc);
+      const int q = chain / p.S, split = chain - q * p.S;
+      const int64_t split_begin = int64_t(split) * p.dps;
+      const int64_t split_end = min(p.N, split_begin + p.dps);
+      const int64_t rb = split_begin + int64_t(step) * item_docs;
+      const int64_t re = min(split_end, rb + item_docs);
+      const int nt = p.ws.q_nt[q];
+      for (int t = lane; t < nt; t += 32) {
+        sh.t_start[t] = p.ws.tq_start[size_t(q) * p.TS + t];
+        sh.t_len[t] = p.ws.tq_len[size_t(q) * p.TS + t];
       }
       __syncwarp();
-      if (lane < gs) {
-        int any = 0;
-        for (int t = 0; t < nt; ++t) any |= (bound[t * (gs + 1) + lane + 1] > bound[t * (gs + 1) + lane]);
-        sh.slab_any[bb][lane] = any;
+      if (step > 0) {
+        spin_until_ge(p.ws.cur_flag + chain, step);
+        for (int t = lane; t < nt; t += 32) sh.t_cur[t] = __ldcg(p.ws.ch_cur + size_t(chain) * p.TS + t);
+      } else {
+        for (int t = lane; t < nt; t += 32)
+          sh.t_cur[t] = split_begin == 0 ? 0 : lower_bound_doc(p.doc_id + sh.t_start[t], 0, sh.t_len[t], split_begin);
       }
       __syncwarp();
-      for (int t = lane; t < nt; t += 32) sh.t_cur[t] = bound[t * (gs + 1) + gs];
+      int gs = nt > 0 ? BM25_BOUND_CAP / nt - 1 : BM25_MAX_GROUP;
+      gs = gs < 1 ? 1 : (gs > BM25_MAX_GROUP ? BM25_MAX_GROUP : gs);
+      const int nslab = rb < re ? int((re - rb + BM25_SLAB - 1) / BM25_SLAB) : 0;
+      const int ngroups = nslab > 0 ? (nslab + gs - 1) / gs : 1;
+      for (int gi = 0; gi < ngroups; ++gi, ++gcount) {
+        const uint32_t bb = gcount & 1;
+        mbar_wait(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
+        Bm25Group& G = sh.grp[bb];
+        const int ns = max(0, min(gs, nslab - gi * gs));
+        const int64_t b0 = rb + int64_t(gi) * gs * BM25_SLAB;
+        if (lane == 0) {
+          G.kind = 0; G.chain = chain; G.step = step; G.first = (gi == 0); G.last = (gi == ngroups - 1);
+          G.final_step = (step == p.steps - 1); G.nt = nt; G.ns = ns; G.b0 = int(b0); G.range_end = int(re);
+        }
+        for (int t = lane; t < nt; t += 32) {
+          G.t_start[t] = sh.t_start[t];
+          G.t_mult[t] = p.ws.tq_mult[size_t(q) * p.TS + t];
+        }
+        if (ns > 0) {
+          for (int w = lane; w < nt * (ns + 1); w += 32) {
+            const int t = w / (ns + 1), j = w % (ns + 1);
+            const int cur = sh.t_cur[t], len = sh.t_len[t];
+            int64_t target = b0 + int64_t(j) * BM25_SLAB;
+            if (target > re) target = re;
+            // ids are strictly increasing inside a term: the answer is at most (target - b0) past cur
+            const int64_t reach = int64_t(cur) + (target - b0);
+            const int hi = int(reach < len ? reach : int64_t(len));
+            G.bound[w] = (j == 0) ? cur : lower_bound_doc(p.doc_id + sh.t_start[t], cur, hi, target);
+          }
+          __syncwarp();
+          if (lane < ns) {
+            int any = 0;
+            for (int t = 0; t < nt; ++t) any |= (G.bound[t * (ns + 1) + lane + 1] > G.bound[t * (ns + 1) + lane]);
+            G.any[lane] = any;
+          }
+          for (int t = lane; t < nt; t += 32) sh.t_cur[t] = G.bound[t * (ns + 1) + ns];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.bfull_bar[bb]);
+      }
+      // publish the cursors for the chain's next item
+      if (step + 1 < p.steps) {
+        for (int t = lane; t < nt; t += 32) p.ws.ch_cur[size_t(chain) * p.TS + t] = sh.t_cur[t];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(p.ws.cur_flag + chain, step + 1);
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.bfull_bar[bb]);
     }
+    const uint32_t bb = gcount & 1;
+    mbar_wait(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
+    if (lane == 0) { sh.grp[bb].kind = 1; mbar_arrive(&sh.bfull_bar[bb]); }
   } else if (warp == BM25_CONSUMERS / 32) {
     // ===================== copy warp: postings -> shared-memory ring =====================
-    // A chunk is emitted once its successor is known (that decides its TERM_END / SLAB_END flags).
     uint32_t c = 0;
-    auto emit = [&](const Bm25Chunk& ch, int flags) {
+    auto stage_acquire = [&]() {
       const uint32_t s = c % BM25_STAGES;
       mbar_wait(&sh.empty_bar[s], ((c / BM25_STAGES) & 1) ^ 1);
       ++c;
-      int skip = 0, cnt4 = 0;
-      float mult = 0.f;
-      if (ch.n > 0) {
-        const int64_t first = sh.t_start[ch.t] + ch.pos;
-        skip = int(first & 3);
-        const int64_t a0 = first - skip;                                   // multiple of 4 elements = 16 bytes
-        const int cnt = ch.n + skip;
-        cnt4 = cnt & ~3;
-        int32_t* dst_id = ring_id + s * BM25_CHUNK;
-        float* dst_imp = ring_imp + s * BM25_CHUNK;
-        // the (at most 3) elements past the last whole 16-byte unit are moved by hand
-        if (lane < cnt - cnt4) {
-          dst_id[cnt4 + lane] = __ldg(p.doc_id + a0 + cnt4 + lane);
-          dst_imp[cnt4 + lane] = __ldg(p.impact + a0 + cnt4 + lane);
-        }
-        mult = sh.t_mult[ch.t];
-        __syncwarp();
-        if (lane == 0) {
-          sh.sdesc[s] = make_int4(ch.n, skip | (flags << 8), __float_as_int(mult), ch.sl0);
-          mbar_arrive_expect_tx(&sh.full_bar[s], uint32_t(cnt4) * 8u);
-          if (cnt4 > 0) {
-            bulk_copy_g2s(dst_id, p.doc_id + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
-            bulk_copy_g2s(dst_imp, p.impact + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
-          }
-        }
-      } else if (lane == 0) {
-        sh.sdesc[s] = make_int4(0, flags << 8, 0, ch.sl0);
+      return s;
+    };
+    // control stage: no postings, just flags and two words for the consumers
+    auto emit_ctrl = [&](int flags, int z, int w) {
+      const uint32_t s = stage_acquire();
+      if (lane == 0) {
+        sh.sdesc[s] = make_int4(0, flags << 8, z, w);
         mbar_arrive(&sh.full_bar[s]);
       }
       __syncwarp();
     };
-    Bm25Chunk pend{-1, 0, 0, 0};
+    auto emit = [&](const Bm25Chunk& ch, int flags) {
+      if (ch.n <= 0) { emit_ctrl(flags, 0, ch.sl0); return; }
+      const uint32_t s = stage_acquire();
+      const int skip = int(ch.first & 3);
+      const int64_t a0 = ch.first - skip;                                  // multiple of 4 elements = 16 bytes
+      const int cnt = ch.n + skip;
+      const int cnt4 = cnt & ~3;
+      int32_t* dst_id = ring_id + s * BM25_CHUNK;
+      float* dst_imp = ring_imp + s * BM25_CHUNK;
+      // the (at most 3) elements past the last whole 16-byte unit are moved by hand
+      if (lane < cnt - cnt4) {
+        dst_id[cnt4 + lane] = __ldg(p.doc_id + a0 + cnt4 + lane);
+        dst_imp[cnt4 + lane] = __ldg(p.impact + a0 + cnt4 + lane);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        sh.sdesc[s] = make_int4(ch.n, skip | (flags << 8), __float_as_int(ch.mult), ch.sl0);
+        mbar_arrive_expect_tx(&sh.full_bar[s], uint32_t(cnt4) * 8u);
+        if (cnt4 > 0) {
+          bulk_copy_g2s(dst_id, p.doc_id + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
+          bulk_copy_g2s(dst_imp, p.impact + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
+        }
+      }
+      __syncwarp();
+    };
+    // A chunk is emitted once its successor is known (that decides its TERM_END / SLAB_END flags).
+    Bm25Chunk pend{0, 0.f, 0, 0, -1};
     bool have = false;
     auto push = [&](const Bm25Chunk& ch) {
       if (have) {
         const bool slab_end = pend.sl0 != ch.sl0;
-        emit(pend, (slab_end ? (BM25_F_SLAB_END | BM25_F_TERM_END) : 0) | ((slab_end || pend.t != ch.t) ? BM25_F_TERM_END : 0));
+        emit(pend, slab_end ? (BM25_F_SLAB_END | BM25_F_TERM_END) : (pend.t != ch.t ? BM25_F_TERM_END : 0));
       }
       pend = ch;
       have = true;
     };
-    uint32_t g = 0;
-    for (int64_t b0 = range_begin; b0 < range_end; b0 += group_docs, ++g) {
-      const uint32_t bb = g & 1;
-      mbar_wait(&sh.bfull_bar[bb], (g >> 1) & 1);
-      const int32_t* bound = sh.bound[bb];
-      const int32_t* any = sh.slab_any[bb];
-      for (int j = 0; j < gs; ++j) {
-        const int64_t slab0 = b0 + int64_t(j) * BM25_SLAB;
-        if (slab0 >= range_end) break;
-        if (!any[j]) {
-          if (!p.nonneg) push(Bm25Chunk{-1, 0, 0, int(slab0)});   // a slab of zero scores still has to be ranked
+    for (uint32_t gc = 0;; ++gc) {
+      const uint32_t bb = gc & 1;
+      mbar_wait(&sh.bfull_bar[bb], (gc >> 1) & 1);
+      const Bm25Group& G = sh.grp[bb];
+      if (G.kind != 0) { emit_ctrl(BM25_F_END, 0, 0); break; }
+      const int nt = G.nt, ns = G.ns, chain = G.chain, step = G.step;
+      if (G.first) emit_ctrl(BM25_F_ITEM_BEGIN, step, chain);
+      for (int j = 0; j < ns; ++j) {
+        const int sl0 = G.b0 + j * BM25_SLAB;
+        if (!G.any[j]) {
+          if (!p.nonneg) push(Bm25Chunk{0, 0.f, 0, sl0, -1});   // a slab of zero scores still has to be ranked
           continue;
         }
         for (int t = 0; t < nt; ++t) {
-          const int lo = bound[t * (gs + 1) + j], hi = bound[t * (gs + 1) + j + 1];
+          const int lo = G.bound[t * (ns + 1) + j], hi = G.bound[t * (ns + 1) + j + 1];
+          const int64_t ts = G.t_start[t];
+          const float mult = G.t_mult[t];
           for (int pos = lo; pos < hi;) {
-            const int skip = int((sh.t_start[t] + pos) & 3);
+            const int skip = int((ts + pos) & 3);
             const int n = min(hi - pos, BM25_CHUNK - skip);
-            push(Bm25Chunk{t, pos, n, int(slab0)});
+            push(Bm25Chunk{ts + pos, mult, n, sl0, t});
             pos += n;
           }
         }
       }
+      if (G.last) {
+        if (have) { emit(pend, BM25_F_TERM_END | BM25_F_SLAB_END); have = false; }
+        emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain);
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);   // `pend` holds copies, not references into bound[]
+      if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);   // `pend` holds copies, nothing points into the group buffer
     }
-    if (have) emit(pend, BM25_F_TERM_END | BM25_F_SLAB_END | BM25_F_END);
-    else emit(Bm25Chunk{-1, 0, 0, 0}, BM25_F_END);
   } else {
     // ===================== consumers =====================
     float mx = -INFINITY;     // largest score this thread wrote into the current slab
+    int64_t range_end = 0;    // docs at or past the end of the chain's split are not ranked
     for (uint32_t c = 0;; ++c) {
       const uint32_t s = c % BM25_STAGES;
       mbar_wait(&sh.full_bar[s], (c / BM25_STAGES) & 1);
       const int4 de = sh.sdesc[s];
       const int n = de.x, skip = de.y & 0xff, flags = de.y >> 8, sl0 = de.w;
-      const float mult = __int_as_float(de.z);
-      {
+      if (n > 0) {
+        const float mult = __int_as_float(de.z);
         const int32_t* ids = ring_id + s * BM25_CHUNK + skip;
         const float* imp = ring_imp + s * BM25_CHUNK + skip;
         float* accr = acc - sl0;                   // accr[doc] == acc[doc - slab0]
@@ -338,6 +457,7 @@ bm25_scan_kernel(const Bm25Params p) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.empty_bar[s]);     // this warp is done reading the stage
+
       if (flags & BM25_F_SLAB_END) {
         const int64_t slab0 = sl0;
         const int cnt_before = sh.cand_cnt;
@@ -406,31 +526,61 @@ bm25_scan_kernel(const Bm25Params p) {
       } else if (flags & BM25_F_TERM_END) {
         cbar();   // the next term may touch the docs this one did
       }
+
+      if (flags & BM25_F_ITEM_BEGIN) {
+        // the previous item ended behind a barrier: the candidate buffer is free
+        const int chain = de.w, step = de.z;
+        const int split = chain % p.S;
+        range_end = min(p.N, int64_t(split + 1) * p.dps);
+        if (step == 0) {
+          if (tid == 0) { sh.cand_cnt = 0; sh.thr_key = thr_init; }
+        } else {
+          spin_until_ge(p.ws.cand_flag + chain, step);
+          const int cnt = __ldcg(p.ws.ch_cnt + chain);
+          const uint64_t* src = p.ws.ch_cand + size_t(chain) * cap;
+          for (int i = tid; i < cnt; i += BM25_CONSUMERS) cand[i] = __ldcg(src + i);
+          if (tid == 0) { sh.cand_cnt = cnt; sh.thr_key = __ldcg(p.ws.ch_thr + chain); }
+        }
+        cbar();
+      }
+      if (flags & BM25_F_ITEM_END) {
+        const int chain = de.w, step = de.z;
+        if (flags & BM25_F_FINAL) {
+          // ---- sorted top-k of the surviving candidates -> this chain's key list ----
+          const int ncand = min(sh.cand_cnt, cap);
+          Bm25Cands cands{cand, ncand};
+          const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
+          uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acc);      // the (zeroed) slab doubles as the sort buffer
+          const int P = p.P;
+          if (tid == 0) sh.sel.nsel = 0;
+          cbar();
+          for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
+            const uint64_t key = cand[i];
+            if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
+          }
+          cbar();
+          block_sort_desc(sortbuf, P, cbar);
+          uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
+          for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
+          cbar();
+          for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
+          cbar();
+        } else {
+          const int cnt = min(sh.cand_cnt, cap);
+          uint64_t* dst = p.ws.ch_cand + size_t(chain) * cap;
+          for (int i = tid; i < cnt; i += BM25_CONSUMERS) dst[i] = cand[i];
+          if (tid == 0) { p.ws.ch_cnt[chain] = cnt; p.ws.ch_thr[chain] = sh.thr_key; }
+          __threadfence();
+          cbar();
+          if (tid == 0) st_release(p.ws.cand_flag + chain, step + 1);
+        }
+      }
       if (flags & BM25_F_END) break;
     }
-
-    // ---- sorted top-k of the surviving candidates -> this (query, range)'s key list ----
-    cbar();
-    const int ncand = min(sh.cand_cnt, cap);
-    Bm25Cands cands{cand, ncand};
-    const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
-    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acc);      // the slab doubles as the sort buffer
-    const int P = p.P;
-    for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;
-    if (tid == 0) sh.sel.nsel = 0;
-    cbar();
-    for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
-      const uint64_t key = cand[i];
-      if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
-    }
-    cbar();
-    block_sort_desc(sortbuf, P, cbar);
-    uint64_t* out = p.out_keys + (size_t(q) * p.nsplit + r) * p.k;
-    for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
   }
 }
 
-// Merge the per-range key lists of one query; when impacts are non-negative, documents that matched
+// Merge the per-split key lists of one query; when impacts are non-negative, documents that matched
 // nothing score 0 and follow the matched ones in ascending id order (bm25_retriever.py:75 keeps them).
 struct Bm25Lists {
   const uint64_t* keys; int n;
@@ -469,23 +619,61 @@ bm25_merge_kernel(const uint64_t* keys, int nsplit, int k, int P, int64_t N, int
   }
 }
 
-struct Bm25Plan { int nsplit, cap, P; int64_t docs_per_split; size_t smem, ws; };
+struct Bm25Plan {
+  int S, cap, P, TS, item_slabs, steps, nc;
+  int64_t dps;
+  unsigned long long total_items;
+  size_t smem, ws;
+  size_t off[12];
+};
 
-static Bm25Plan bm25_plan(int64_t N, int nq, int k, int sms) {
+static int g_item_slabs = 0;     // 0 = not yet initialised
+static int bm25_item_slabs() {
+  if (!g_item_slabs) {
+    const char* e = getenv("LRAG_BM25_ITEM_SLABS");   // tuning knob: docs per work item = value * 16384
+    const int v = e ? atoi(e) : BM25_DEFAULT_ITEM_SLABS;
+    g_item_slabs = (v < 1 || v > 4096) ? BM25_DEFAULT_ITEM_SLABS : v;
+  }
+  return g_item_slabs;
+}
+
+static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int sms) {
   Bm25Plan pl;
   pl.P = next_pow2(k);
   pl.cap = 2 * pl.P < 1024 ? 1024 : 2 * pl.P;        // <= 2048 = 4 * BM25_CONSUMERS
-  const int64_t nslab = (N + BM25_SLAB - 1) / BM25_SLAB;
-  int64_t want = (int64_t(4) * sms + nq - 1) / nq;   // enough CTAs to fill the machine twice over
-  if (want < 1) want = 1;
-  if (want > nslab) want = nslab > 0 ? nslab : 1;
-  int64_t slabs_per = (nslab + want - 1) / want;
-  if (slabs_per < 1) slabs_per = 1;
-  pl.docs_per_split = slabs_per * BM25_SLAB;
-  pl.nsplit = int((N + pl.docs_per_split - 1) / pl.docs_per_split);
-  if (pl.nsplit < 1) pl.nsplit = 1;
+  pl.TS = int(max_query_terms < 1 ? 1 : (max_query_terms > BM25_MAXT ? BM25_MAXT : max_query_terms));
+  pl.item_slabs = bm25_item_slabs();
+  const int64_t item_docs = int64_t(pl.item_slabs) * BM25_SLAB;
+  int64_t n_items = (N + item_docs - 1) / item_docs;
+  if (n_items < 1) n_items = 1;
+  // few queries: split every query's doc range into independent chains so that the machine is full
+  const int64_t resident = 2 * int64_t(sms);
+  int64_t S = 1;
+  if (nq < 2 * resident) { S = (2 * resident + nq - 1) / nq; if (S > n_items) S = n_items; }
+  const int64_t items_per_split = (n_items + S - 1) / S;
+  pl.dps = items_per_split * item_docs;
+  S = (N + pl.dps - 1) / pl.dps;
+  if (S < 1) S = 1;
+  pl.S = int(S);
+  pl.steps = int(items_per_split);
+  pl.nc = int(int64_t(nq) * S);
+  pl.total_items = (unsigned long long)pl.steps * (unsigned long long)pl.nc;
   pl.smem = size_t(BM25_SLAB) * 4 + BM25_RING_BYTES + size_t(pl.cap) * 8 + sizeof(Bm25Shared);
-  pl.ws = align_up(size_t(nq) * pl.nsplit * k * 8, 256);
+  size_t o = 0;
+  auto take = [&](int i, size_t bytes) { pl.off[i] = o; o += align_up(bytes, 256); };
+  take(0, 8);                                         // counter
+  take(1, size_t(pl.nc) * 4);                         // cur_flag
+  take(2, size_t(pl.nc) * 4);                         // cand_flag
+  take(3, size_t(nq) * 4);                            // q_nt
+  take(4, size_t(nq) * pl.TS * 8);                    // tq_start
+  take(5, size_t(nq) * pl.TS * 4);                    // tq_len
+  take(6, size_t(nq) * pl.TS * 4);                    // tq_mult
+  take(7, size_t(pl.nc) * pl.TS * 4);                 // ch_cur
+  take(8, size_t(pl.nc) * 8);                         // ch_thr
+  take(9, size_t(pl.nc) * 4);                         // ch_cnt
+  take(10, pl.steps > 1 ? size_t(pl.nc) * pl.cap * 8 : 8);   // ch_cand
+  take(11, size_t(pl.nc) * k * 8);                    // out_keys
+  pl.ws = o;
   return pl;
 }
 
@@ -493,10 +681,15 @@ static Bm25Plan bm25_plan(int64_t N, int nq, int k, int sms) {
 
 using namespace lrag;
 
+extern "C" int lrag_bm25_set_item_slabs(int slabs) {
+  LRAG_REQUIRE(slabs >= 0 && slabs <= 4096, "bm25_set_item_slabs: %d out of range (0 = default, max 4096)", slabs);
+  g_item_slabs = slabs ? slabs : BM25_DEFAULT_ITEM_SLABS;
+  return LRAG_OK;
+}
+
 extern "C" size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms) {
-  (void)max_query_terms;
   if (N < 0 || nq <= 0 || k <= 0) return 0;
-  return bm25_plan(N, nq, k, sm_count()).ws;
+  return bm25_plan(N, nq, k, max_query_terms, sm_count()).ws;
 }
 
 extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
@@ -506,7 +699,7 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && k > 0 && k <= LRAG_MAX_K, "bm25_topk: need nq > 0 and 1 <= k <= %d (nq=%d k=%d)", LRAG_MAX_K, nq, k);
-  LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31), "bm25_topk: N=%lld out of range for one shard", (long long)N);
+  LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31) - BM25_SLAB, "bm25_topk: N=%lld out of range for one shard", (long long)N);
   LRAG_REQUIRE(V >= 0 && V < (int64_t(1) << 31) && nnz >= 0, "bm25_topk: V=%lld nnz=%lld out of range", (long long)V, (long long)nnz);
   LRAG_REQUIRE(max_query_terms >= 0 && max_query_terms <= LRAG_BM25_MAX_QUERY_TERMS,
                "bm25_topk: a query has %lld terms; at most %d are supported", (long long)max_query_terms,
@@ -514,22 +707,46 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   LRAG_REQUIRE(indptr && q_indptr && out_score && out_id, "bm25_topk: null pointer");
   LRAG_REQUIRE((reinterpret_cast<uintptr_t>(doc_id) & 15) == 0 && (reinterpret_cast<uintptr_t>(impact) & 15) == 0,
                "bm25_topk: doc_id and impact must be 16-byte aligned (bulk async copies)");
-  const Bm25Plan pl = bm25_plan(N, nq, k, sm_count());
+  const int sms = sm_count();
+  const Bm25Plan pl = bm25_plan(N, nq, k, max_query_terms, sms);
   if (ws_bytes < pl.ws || !ws) { set_error("bm25_topk: workspace %zu < required %zu", ws_bytes, pl.ws); return LRAG_ENOSPC; }
+  LRAG_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "bm25_topk: workspace must be 16-byte aligned");
+  uint8_t* w = static_cast<uint8_t*>(ws);
   Bm25Params p;
   p.indptr = indptr; p.doc_id = doc_id; p.impact = impact; p.V = V; p.nnz = nnz; p.q_indptr = q_indptr; p.q_term = q_term;
-  p.N = N; p.docs_per_split = pl.docs_per_split; p.nq = nq; p.k = k; p.nonneg = nonneg ? 1 : 0;
-  p.nsplit = pl.nsplit; p.cap = pl.cap; p.P = pl.P; p.out_keys = static_cast<uint64_t*>(ws);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LRAG_CHECK_CUDA(cudaFuncSetAttribute(bm25_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 118 * 1024));
-    attr_set = true;
+  p.N = N; p.dps = pl.dps; p.total_items = pl.total_items; p.nq = nq; p.k = k; p.nonneg = nonneg ? 1 : 0;
+  p.S = pl.S; p.cap = pl.cap; p.P = pl.P; p.TS = pl.TS; p.item_slabs = pl.item_slabs; p.steps = pl.steps; p.nc = pl.nc;
+  p.ws.counter = reinterpret_cast<unsigned long long*>(w + pl.off[0]);
+  p.ws.cur_flag = reinterpret_cast<int*>(w + pl.off[1]);
+  p.ws.cand_flag = reinterpret_cast<int*>(w + pl.off[2]);
+  p.ws.q_nt = reinterpret_cast<int*>(w + pl.off[3]);
+  p.ws.tq_start = reinterpret_cast<int64_t*>(w + pl.off[4]);
+  p.ws.tq_len = reinterpret_cast<int32_t*>(w + pl.off[5]);
+  p.ws.tq_mult = reinterpret_cast<float*>(w + pl.off[6]);
+  p.ws.ch_cur = reinterpret_cast<int32_t*>(w + pl.off[7]);
+  p.ws.ch_thr = reinterpret_cast<unsigned long long*>(w + pl.off[8]);
+  p.ws.ch_cnt = reinterpret_cast<int*>(w + pl.off[9]);
+  p.ws.ch_cand = reinterpret_cast<uint64_t*>(w + pl.off[10]);
+  p.ws.out_keys = reinterpret_cast<uint64_t*>(w + pl.off[11]);
+
+  static size_t smem_set = 0;
+  if (pl.smem > smem_set) {
+    LRAG_CHECK_CUDA(cudaFuncSetAttribute(bm25_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
+    smem_set = pl.smem;
   }
+  int occ = 0;
+  LRAG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem));
+  LRAG_REQUIRE(occ >= 1, "bm25_topk: the scan kernel does not fit on an SM (smem %zu)", pl.smem);
+  unsigned long long grid = (unsigned long long)occ * sms;
+  if (grid > pl.total_items) grid = pl.total_items;
+  const int prep_blocks = int(std::min<int64_t>((int64_t(nq) + 7) / 8, 4 * int64_t(sms)));
+  bm25_prepare_kernel<<<prep_blocks, 256, 0, stream>>>(p);
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   prof_begin(stream, PROF_BM25_SCAN);
-  bm25_scan_kernel<<<unsigned(int64_t(nq) * pl.nsplit), BM25_THREADS, pl.smem, stream>>>(p);
+  bm25_scan_kernel<<<unsigned(grid), BM25_THREADS, pl.smem, stream>>>(p);
   prof_end(stream);
   LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
-  bm25_merge_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p.out_keys, pl.nsplit, k, pl.P, N, id_base,
+  bm25_merge_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(p.ws.out_keys, pl.S, k, pl.P, N, id_base,
                                                                           p.nonneg, out_score, out_id);
   LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
   return LRAG_OK;

@@ -125,6 +125,11 @@ class Bm25DeviceIndex:
         return int(self.doc_id.numel())
 
 
+def bm25_set_item_slabs(slabs: int) -> None:
+    """Tuning knob of the BM25 scan: documents per work item = slabs * 16384 (0 = default)."""
+    check(_native.load().lrag_bm25_set_item_slabs(int(slabs)), "lrag_bm25_set_item_slabs")
+
+
 def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int, k: int):
     """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV)."""
     lib = _native.init(index.indptr.device.index)

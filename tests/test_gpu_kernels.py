@@ -210,14 +210,26 @@ def test_bm25_synthetic_multi_slab_and_split(eng):
     queries = [rng.choice(V, size=int(rng.integers(2, 9)), p=p).tolist() for _ in range(12)]
     queries.append([V - 1, V - 2])                    # rare terms only: sparse slabs are skipped
     queries.append([int(np.argmin(np.diff(host.indptr) + (np.diff(host.indptr) == 0) * 10 ** 9))])  # rarest term
-    for k in (100, 1000):
-        s, i = _run_bm25(eng, host, queries, k)
+    # (k, item slabs, query repetitions): 14 queries over 600k docs split every query into chains of one
+    # item; 1-slab items with 700 queries make every chain hand its state over 37 times
+    for k, item_slabs, reps in ((100, 0, 1), (1000, 0, 1), (100, 1, 50), (100, 3, 50)):
+        eng.bm25_set_item_slabs(item_slabs)
+        try:
+            s, i = _run_bm25(eng, host, queries * reps, k)
+        finally:
+            eng.bm25_set_item_slabs(0)
         s, i = s.cpu().numpy(), i.cpu().numpy()
+        if reps > 1:      # identical queries give identical rows whichever CTA ran their items
+            for r in range(1, reps):
+                sl = slice(r * len(queries), (r + 1) * len(queries))
+                np.testing.assert_array_equal(i[sl], i[:len(queries)])
+                np.testing.assert_array_equal(s[sl], s[:len(queries)])
+            s, i = s[:len(queries)], i[:len(queries)]
         m = k + 50
         O_s = np.zeros((len(queries), m)); O_i = np.zeros((len(queries), m), dtype=np.int64)
         for q, toks in enumerate(queries):
             O_s[q], O_i[q] = csr.search(toks, m)
-        check_topk_parity(s, i, O_s, O_i, k, TAU_FP32, what=f"bm25-synth-k{k}")
+        check_topk_parity(s, i, O_s, O_i, k, TAU_FP32, what=f"bm25-synth-k{k}-items{item_slabs}")
     # a shard [lo, hi) with global statistics returns global ids
     lo, hi = 200_000, 450_000
     s, i = _run_bm25(eng, host, queries[:4], 100, lo, hi)
