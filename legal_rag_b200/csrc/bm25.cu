@@ -89,7 +89,7 @@ struct Bm25Group {                 // bounds warp -> copy warp
   int64_t t_start[BM25_MAXT];
   float t_mult[BM25_MAXT];
   int32_t bound[BM25_BOUND_CAP];   // [t * (ns + 1) + j]
-  int32_t any[BM25_MAX_GROUP];
+  int32_t last_t[BM25_MAX_GROUP];  // last term with postings in the slab, -1 = none
 };
 
 struct Bm25Shared {
@@ -134,6 +134,11 @@ __device__ __forceinline__ bool consumers_bar_or(bool pred) {
       : "memory");
   return out != 0;
 }
+
+// shared-memory accesses by 32-bit shared address (one address computation per access)
+__device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -230,9 +235,6 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
   }
 }
 
-// One ring stage worth of postings: [first, first + n) of the arrays, for the slab starting at doc sl0.
-struct Bm25Chunk { int64_t first; float mult; int n, sl0, t; };
-
 __global__ void __launch_bounds__(BM25_THREADS, 2)
 bm25_scan_kernel(const Bm25Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -320,9 +322,9 @@ bm25_scan_kernel(const Bm25Params p) {
           }
           __syncwarp();
           if (lane < ns) {
-            int any = 0;
-            for (int t = 0; t < nt; ++t) any |= (G.bound[t * (ns + 1) + lane + 1] > G.bound[t * (ns + 1) + lane]);
-            G.any[lane] = any;
+            int last = -1;
+            for (int t = 0; t < nt; ++t) if (G.bound[t * (ns + 1) + lane + 1] > G.bound[t * (ns + 1) + lane]) last = t;
+            G.last_t[lane] = last;
           }
           for (int t = lane; t < nt; t += 32) sh.t_cur[t] = G.bound[t * (ns + 1) + ns];
         }
@@ -343,11 +345,13 @@ bm25_scan_kernel(const Bm25Params p) {
     if (lane == 0) { sh.grp[bb].kind = 1; mbar_arrive(&sh.bfull_bar[bb]); }
   } else if (warp == BM25_CONSUMERS / 32) {
     // ===================== copy warp: postings -> shared-memory ring =====================
-    uint32_t c = 0;
+    // Per slab the lanes look up one term's run each; the runs are then issued in term order, one
+    // short serial sequence per chunk (wait for a free stage, descriptor, expect_tx, two bulk copies).
+    uint32_t ps = 0, pph = 1;
     auto stage_acquire = [&]() {
-      const uint32_t s = c % BM25_STAGES;
-      mbar_wait(&sh.empty_bar[s], ((c / BM25_STAGES) & 1) ^ 1);
-      ++c;
+      const uint32_t s = ps;
+      mbar_wait(&sh.empty_bar[s], pph);
+      if (++ps == BM25_STAGES) { ps = 0; pph ^= 1; }
       return s;
     };
     // control stage: no postings, just flags and two words for the consumers
@@ -359,23 +363,27 @@ bm25_scan_kernel(const Bm25Params p) {
       }
       __syncwarp();
     };
-    auto emit = [&](const Bm25Chunk& ch, int flags) {
-      if (ch.n <= 0) { emit_ctrl(flags, 0, ch.sl0); return; }
+    // postings [first, first + n) -> one stage.  The copy window is widened to 16-byte units; the
+    // consumers ignore what lies outside [skip, skip + n).
+    auto emit = [&](int64_t first, int n, float mult, int sl0, int flags) {
       const uint32_t s = stage_acquire();
-      const int skip = int(ch.first & 3);
-      const int64_t a0 = ch.first - skip;                                  // multiple of 4 elements = 16 bytes
-      const int cnt = ch.n + skip;
-      const int cnt4 = cnt & ~3;
+      const int skip = int(first & 3);
+      const int64_t a0 = first - skip;
+      int cnt4 = (n + skip + 3) & ~3;
       int32_t* dst_id = ring_id + s * BM25_CHUNK;
       float* dst_imp = ring_imp + s * BM25_CHUNK;
-      // the (at most 3) elements past the last whole 16-byte unit are moved by hand
-      if (lane < cnt - cnt4) {
-        dst_id[cnt4 + lane] = __ldg(p.doc_id + a0 + cnt4 + lane);
-        dst_imp[cnt4 + lane] = __ldg(p.impact + a0 + cnt4 + lane);
+      if (a0 + cnt4 > p.nnz) {
+        // the arrays end inside the last unit: those (at most 3) postings are moved by hand
+        cnt4 -= 4;
+        const int tail = int(p.nnz - (a0 + cnt4));
+        if (lane < tail) {
+          dst_id[cnt4 + lane] = __ldg(p.doc_id + a0 + cnt4 + lane);
+          dst_imp[cnt4 + lane] = __ldg(p.impact + a0 + cnt4 + lane);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       if (lane == 0) {
-        sh.sdesc[s] = make_int4(ch.n, skip | (flags << 8), __float_as_int(ch.mult), ch.sl0);
+        sh.sdesc[s] = make_int4(n, skip | (flags << 8), __float_as_int(mult), sl0);
         mbar_arrive_expect_tx(&sh.full_bar[s], uint32_t(cnt4) * 8u);
         if (cnt4 > 0) {
           bulk_copy_g2s(dst_id, p.doc_id + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
@@ -383,17 +391,6 @@ bm25_scan_kernel(const Bm25Params p) {
         }
       }
       __syncwarp();
-    };
-    // A chunk is emitted once its successor is known (that decides its TERM_END / SLAB_END flags).
-    Bm25Chunk pend{0, 0.f, 0, 0, -1};
-    bool have = false;
-    auto push = [&](const Bm25Chunk& ch) {
-      if (have) {
-        const bool slab_end = pend.sl0 != ch.sl0;
-        emit(pend, slab_end ? (BM25_F_SLAB_END | BM25_F_TERM_END) : (pend.t != ch.t ? BM25_F_TERM_END : 0));
-      }
-      pend = ch;
-      have = true;
     };
     for (uint32_t gc = 0;; ++gc) {
       const uint32_t bb = gc & 1;
@@ -404,59 +401,89 @@ bm25_scan_kernel(const Bm25Params p) {
       if (G.first) emit_ctrl(BM25_F_ITEM_BEGIN, step, chain);
       for (int j = 0; j < ns; ++j) {
         const int sl0 = G.b0 + j * BM25_SLAB;
-        if (!G.any[j]) {
-          if (!p.nonneg) push(Bm25Chunk{0, 0.f, 0, sl0, -1});   // a slab of zero scores still has to be ranked
+        const int last_t = G.last_t[j];
+        if (last_t < 0) {
+          // no postings here; with negative impacts a slab of zero scores still has to be ranked
+          if (!p.nonneg) emit_ctrl(BM25_F_SLAB_END | BM25_F_TERM_END, 0, sl0);
           continue;
         }
-        for (int t = 0; t < nt; ++t) {
-          const int lo = G.bound[t * (ns + 1) + j], hi = G.bound[t * (ns + 1) + j + 1];
-          const int64_t ts = G.t_start[t];
-          const float mult = G.t_mult[t];
-          for (int pos = lo; pos < hi;) {
-            const int skip = int((ts + pos) & 3);
-            const int n = min(hi - pos, BM25_CHUNK - skip);
-            push(Bm25Chunk{ts + pos, mult, n, sl0, t});
-            pos += n;
+        for (int t0 = 0; t0 <= last_t; t0 += 32) {
+          const int t = t0 + lane;
+          int64_t first = 0; int cnt = 0; float mult = 0.f;
+          if (t <= last_t) {
+            const int lo = G.bound[t * (ns + 1) + j];
+            cnt = G.bound[t * (ns + 1) + j + 1] - lo;
+            first = G.t_start[t] + lo;
+            mult = G.t_mult[t];
+          }
+          uint32_t live = __ballot_sync(0xffffffffu, cnt > 0);
+          while (live) {
+            const int src = __ffs(live) - 1;
+            live &= live - 1;
+            int64_t pos = __shfl_sync(0xffffffffu, first, src);
+            int rem = __shfl_sync(0xffffffffu, cnt, src);
+            const float m = __shfl_sync(0xffffffffu, mult, src);
+            const int endflags = BM25_F_TERM_END | ((t0 + src == last_t) ? BM25_F_SLAB_END : 0);
+            while (rem > 0) {
+              const int n = min(rem, BM25_CHUNK - int(pos & 3));
+              emit(pos, n, m, sl0, n == rem ? endflags : 0);
+              pos += n;
+              rem -= n;
+            }
           }
         }
       }
-      if (G.last) {
-        if (have) { emit(pend, BM25_F_TERM_END | BM25_F_SLAB_END); have = false; }
-        emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain);
-      }
+      if (G.last) emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);   // `pend` holds copies, nothing points into the group buffer
+      if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);
     }
   } else {
     // ===================== consumers =====================
     float mx = -INFINITY;     // largest score this thread wrote into the current slab
     int64_t range_end = 0;    // docs at or past the end of the chain's split are not ranked
-    for (uint32_t c = 0;; ++c) {
-      const uint32_t s = c % BM25_STAGES;
-      mbar_wait(&sh.full_bar[s], (c / BM25_STAGES) & 1);
+    const uint32_t acc_u32 = smem_u32(acc);
+    const uint32_t rid0 = smem_u32(ring_id) + tid * 4, rim0 = smem_u32(ring_imp) + tid * 4;
+    uint32_t s = 0, ph = 0;
+    for (;;) {
+      mbar_wait(&sh.full_bar[s], ph);
       const int4 de = sh.sdesc[s];
-      const int n = de.x, skip = de.y & 0xff, flags = de.y >> 8, sl0 = de.w;
-      if (n > 0) {
-        const float mult = __int_as_float(de.z);
-        const int32_t* ids = ring_id + s * BM25_CHUNK + skip;
-        const float* imp = ring_imp + s * BM25_CHUNK + skip;
-        float* accr = acc - sl0;                   // accr[doc] == acc[doc - slab0]
-        int d[BM25_PER_THREAD]; float v[BM25_PER_THREAD], a[BM25_PER_THREAD];
+      const int n = de.x, flags = de.y >> 8, sl0 = de.w;
+      const float mult = __int_as_float(de.z);
+      const uint32_t accb = acc_u32 - 4u * uint32_t(sl0);        // accb + 4 * doc == &acc[doc - slab0]
+      const uint32_t rid = rid0 + s * (BM25_CHUNK * 4), rim = rim0 + s * (BM25_CHUNK * 4);
+      int d[BM25_PER_THREAD]; float v[BM25_PER_THREAD], a[BM25_PER_THREAD];
+      if (n == BM25_CHUNK) {
+        // whole stage: no predicates.  The stage is handed back as soon as it is in registers.
+#pragma unroll
+        for (int u = 0; u < BM25_PER_THREAD; ++u) { d[u] = lds_s32(rid + u * (BM25_CONSUMERS * 4)); v[u] = lds_f32(rim + u * (BM25_CONSUMERS * 4)); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
+#pragma unroll
+        for (int u = 0; u < BM25_PER_THREAD; ++u) a[u] = lds_f32(accb + 4u * uint32_t(d[u]));
 #pragma unroll
         for (int u = 0; u < BM25_PER_THREAD; ++u) {
-          const int i = tid + u * BM25_CONSUMERS;
-          const bool ok = i < n;
-          d[u] = ok ? ids[i] : -1;
-          v[u] = ok ? imp[i] : 0.f;
+          a[u] = fmaf(mult, v[u], a[u]);
+          sts_f32(accb + 4u * uint32_t(d[u]), a[u]);
+          mx = fmaxf(mx, a[u]);
         }
+      } else {
+        const int skip = de.y & 0xff;
 #pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) a[u] = (d[u] >= 0) ? accr[d[u]] : 0.f;
+        for (int u = 0; u < BM25_PER_THREAD; ++u) {
+          const bool ok = tid + u * BM25_CONSUMERS < n;
+          d[u] = ok ? lds_s32(rid + (skip + u * BM25_CONSUMERS) * 4) : -1;
+          v[u] = ok ? lds_f32(rim + (skip + u * BM25_CONSUMERS) * 4) : 0.f;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
+#pragma unroll
+        for (int u = 0; u < BM25_PER_THREAD; ++u) a[u] = (d[u] >= 0) ? lds_f32(accb + 4u * uint32_t(d[u])) : 0.f;
 #pragma unroll
         for (int u = 0; u < BM25_PER_THREAD; ++u)
-          if (d[u] >= 0) { a[u] = fmaf(mult, v[u], a[u]); accr[d[u]] = a[u]; mx = fmaxf(mx, a[u]); }
+          if (d[u] >= 0) { a[u] = fmaf(mult, v[u], a[u]); sts_f32(accb + 4u * uint32_t(d[u]), a[u]); mx = fmaxf(mx, a[u]); }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.empty_bar[s]);     // this warp is done reading the stage
+      if (++s == BM25_STAGES) { s = 0; ph ^= 1; }
+      if (flags == 0) continue;
 
       if (flags & BM25_F_SLAB_END) {
         const int64_t slab0 = sl0;
