@@ -114,7 +114,12 @@ int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
  * `max_query_terms` = the longest query's token count (host-side knowledge of q_indptr; at most
  * LRAG_BM25_MAX_QUERY_TERMS).  `nonneg` != 0 asserts every impact >= 0 (true whenever the corpus'
  * average idf is positive): doc slabs no query term touches are then skipped and zero-score
- * documents are filled in by id; with nonneg == 0 every document of every slab is ranked. */
+ * documents are filled in by id; with nonneg == 0 every document of every slab is ranked.
+ * `impact_bound` >= max |impact[p]| over the index (compute it once when the index is built):
+ * scores are accumulated in int32 fixed point with a per-query power-of-two scale chosen so that
+ * impact_bound * (tokens of the query) stays below 2^30 -- at least 2^-22 absolute resolution for
+ * an 8-token query with impacts up to 30 -- which makes the sums exact, order-independent and
+ * reproducible; a bound that is too small lets a score overflow. */
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
 /* Tuning knob (process-wide; call before sizing the workspace): documents per work item =
  * slabs * 16384.  Small items keep the posting ranges all queries are working on inside L2;
@@ -123,8 +128,8 @@ size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_quer
 int lrag_bm25_set_item_slabs(int slabs);
 int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,
                    int64_t nnz, const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
-                   int64_t N, int k, int64_t id_base, int nonneg, float* out_score, int64_t* out_id,
-                   void* ws, size_t ws_bytes, lrag_stream_t stream);
+                   int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
+                   int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * ColBERT channel.  Replaces the scoring inside `Searcher.search(query, k)` at

@@ -24,19 +24,22 @@
 //                      aligned source windows) that complete on mbarriers.  Each ring stage carries a
 //                      descriptor {count, skip, term multiplicity, slab base, flags}: the consumers
 //                      are a plain interpreter of that stream;
-//   * 16 consumer warps -- per stage add `mult * impact` into acc[doc - slab0] and keep a per-thread
-//                      running max of what they wrote.  Doc ids are unique inside a term, so a
-//                      term's adds never collide and need no atomics; a named barrier separates terms
-//                      (flag TERM_END).  At SLAB_END one `bar.red.or` tells whether any thread wrote
-//                      a score that reaches the query's running k-th best: only then is the slab
-//                      scanned for candidates (appended to a shared buffer; an overflow triggers an
-//                      exact radix select that raises the threshold).  The slab is re-zeroed.
+//   * 16 consumer warps -- per stage add `mult * impact` into acc[doc - slab0] with one shared-memory
+//                      integer atomic per posting: scores are kept in fixed point (int32, a per-query
+//                      power-of-two scale sized from `impact_bound`), so adds commute exactly, the
+//                      terms of a slab need no barrier between them and the result is independent
+//                      of scheduling.  Each thread keeps a running max of what it wrote.  At
+//                      SLAB_END one `bar.red.or` tells whether any thread wrote a score that reaches
+//                      the query's running k-th best: only then is the slab scanned for candidates
+//                      (appended to a shared buffer; an overflow triggers an exact radix select that
+//                      raises the threshold).  The slab is re-zeroed.
 //                      ITEM_BEGIN / ITEM_END stages load / store the chain's candidate state; the
 //                      chain's last item sorts its top-k into the per-chain key list.
 // Slabs in which no query term has a posting are skipped when impacts are known non-negative;
 // documents that match nothing (score 0) are then added by the merge step, lowest id first, exactly
 // as the reference's stable sort does.  bm25_merge_kernel merges the per-split lists of a query.
 #include <algorithm>
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,7 +48,8 @@
 namespace lrag {
 
 constexpr int BM25_CONSUMERS = 512;                  // 16 warps
-constexpr int BM25_THREADS = BM25_CONSUMERS + 64;    // + copy warp (16) + bounds warp (17)
+constexpr int BM25_COPY_WARPS = 2;                   // chunk c is issued by copy warp c % BM25_COPY_WARPS
+constexpr int BM25_THREADS = BM25_CONSUMERS + 32 * BM25_COPY_WARPS + 32;   // consumers, copy warps, bounds warp
 constexpr int BM25_SLAB = 16384;
 constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (fewer when a query has many terms)
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
@@ -55,8 +59,8 @@ constexpr int BM25_STAGES = 3;                       // 64 KB slab + 24 KB ring 
 constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
-constexpr int BM25_DEFAULT_ITEM_SLABS = 8;
-enum : int { BM25_F_TERM_END = 1, BM25_F_SLAB_END = 2, BM25_F_ITEM_BEGIN = 4, BM25_F_ITEM_END = 8, BM25_F_FINAL = 16, BM25_F_END = 32 };
+constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
+enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
 
 struct Bm25Ws {
   unsigned long long* counter;     // next item
@@ -65,7 +69,8 @@ struct Bm25Ws {
   int* q_nt;                       // [nq] distinct in-vocabulary terms with postings
   int64_t* tq_start;               // [nq, TS] first posting
   int32_t* tq_len;                 // [nq, TS] df
-  float* tq_mult;                  // [nq, TS] occurrences in the query
+  float* tq_mult;                  // [nq, TS] occurrences in the query x the query's fixed-point scale
+  float* q_inv_scale;              // [nq] 1 / scale
   int32_t* ch_cur;                 // [nc, TS] postings consumed so far (relative to tq_start)
   unsigned long long* ch_thr;      // [nc]
   int* ch_cnt;                     // [nc]
@@ -79,6 +84,7 @@ struct Bm25Params {
   int64_t N; int64_t dps;          // docs per split (multiple of the item size)
   unsigned long long total_items;
   int nq, k, nonneg, S, cap, P, TS, item_slabs, steps, nc;
+  float impact_bound;              // >= max |impact| over the index
   Bm25Ws ws;
 };
 
@@ -86,6 +92,7 @@ struct Bm25Group {                 // bounds warp -> copy warp
   int kind;                        // 0 = slabs of an item, 1 = no more work
   int chain, step, first, last, final_step, nt, ns;
   int b0, range_end;
+  float inv_scale;
   int64_t t_start[BM25_MAXT];
   float t_mult[BM25_MAXT];
   int32_t bound[BM25_BOUND_CAP];   // [t * (ns + 1) + j]
@@ -94,7 +101,7 @@ struct Bm25Group {                 // bounds warp -> copy warp
 
 struct Bm25Shared {
   SelectShared sel;
-  int4 sdesc[BM25_STAGES];         // {n, skip | flags << 8, mult (float bits) or step, slab0 or chain}
+  int4 sdesc[BM25_STAGES];         // {n | skip << 12 | flags << 16, mult x scale (float bits) or step, slab0 or chain, 1/scale bits}
   uint64_t full_bar[BM25_STAGES], empty_bar[BM25_STAGES];   // posting ring
   uint64_t bfull_bar[2], bempty_bar[2];                      // group buffers
   Bm25Group grp[2];
@@ -138,7 +145,11 @@ __device__ __forceinline__ bool consumers_bar_or(bool pred) {
 // shared-memory accesses by 32-bit shared address (one address computation per access)
 __device__ __forceinline__ int lds_s32(uint32_t a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ int atoms_add_s32(uint32_t a, int v) {
+  int o;
+  asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+  return o;
+}
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -177,13 +188,13 @@ __device__ __forceinline__ void cand_append(bool want, uint64_t key, uint64_t* c
 
 struct Bm25Union {
   const uint64_t* cand; int ncand;
-  const float* acc; int64_t slab0; int64_t range_end; unsigned long long thr_key;
+  const int* acc; float inv_scale; int64_t slab0; int64_t range_end; unsigned long long thr_key;
   template <class F> __device__ void operator()(F&& f) const {
     for (int i = threadIdx.x; i < ncand; i += BM25_CONSUMERS) f(cand[i]);
     for (int i = threadIdx.x; i < BM25_SLAB; i += BM25_CONSUMERS) {
       const int64_t doc = slab0 + i;
       if (doc >= range_end) break;
-      const uint64_t key = make_key(acc[i], uint32_t(doc));
+      const uint64_t key = make_key(float(acc[i]) * inv_scale, uint32_t(doc));
       if (key > thr_key) f(key);
     }
   }
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
     const int64_t qlen = p.q_indptr[q + 1] - qs;
     const int nraw = int(qlen < p.TS ? qlen : p.TS);
     const int32_t* raw = p.q_term + qs;
-    int base = 0;
+    int base = 0, scored = 0;
     for (int r0 = 0; r0 < nraw; r0 += 32) {
       const int i = r0 + lane;
       int t = -1;
@@ -230,8 +241,17 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
         p.ws.tq_mult[slot] = float(mult);
       }
       base += __popc(m);
+      scored += __reduce_add_sync(0xffffffffu, mult);
     }
-    if (lane == 0) p.ws.q_nt[q] = base;
+    // Fixed-point scale of this query's accumulators: a power of two such that no score can reach
+    // 2^30 in magnitude (|score| <= impact_bound x scored tokens).
+    const float bound = fmaxf(p.impact_bound * float(scored > 0 ? scored : 1), 1e-30f);
+    int ex = 29 - ilogbf(bound);                    // bound * 2^ex < 2^30
+    ex = ex > 60 ? 60 : (ex < -60 ? -60 : ex);
+    const float scale = ldexpf(1.0f, ex);
+    __syncwarp();
+    for (int t = lane; t < base; t += 32) p.ws.tq_mult[size_t(q) * p.TS + t] *= scale;
+    if (lane == 0) { p.ws.q_nt[q] = base; p.ws.q_inv_scale[q] = ldexpf(1.0f, -ex); }
   }
 }
 
@@ -253,7 +273,7 @@ bm25_scan_kernel(const Bm25Params p) {
     sh.cand_cnt = 0;
     sh.thr_key = thr_init;
     for (int s = 0; s < BM25_STAGES; ++s) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], BM25_CONSUMERS / 32); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], BM25_COPY_WARPS); }
     fence_barrier_init();
   }
   // zero the slab once; every slab end leaves it zeroed again
@@ -261,7 +281,7 @@ bm25_scan_kernel(const Bm25Params p) {
   __syncthreads();
   const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
 
-  if (warp == BM25_CONSUMERS / 32 + 1) {
+  if (warp == BM25_CONSUMERS / 32 + BM25_COPY_WARPS) {
     // ===================== bounds warp =====================
     const int64_t item_docs = int64_t(p.item_slabs) * BM25_SLAB;
     uint32_t gcount = 0;
@@ -304,6 +324,7 @@ bm25_scan_kernel(const Bm25Params p) {
         if (lane == 0) {
           G.kind = 0; G.chain = chain; G.step = step; G.first = (gi == 0); G.last = (gi == ngroups - 1);
           G.final_step = (step == p.steps - 1); G.nt = nt; G.ns = ns; G.b0 = int(b0); G.range_end = int(re);
+          G.inv_scale = p.ws.q_inv_scale[q];
         }
         for (int t = lane; t < nt; t += 32) {
           G.t_start[t] = sh.t_start[t];
@@ -343,22 +364,29 @@ bm25_scan_kernel(const Bm25Params p) {
     const uint32_t bb = gcount & 1;
     mbar_wait(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
     if (lane == 0) { sh.grp[bb].kind = 1; mbar_arrive(&sh.bfull_bar[bb]); }
-  } else if (warp == BM25_CONSUMERS / 32) {
-    // ===================== copy warp: postings -> shared-memory ring =====================
+  } else if (warp >= BM25_CONSUMERS / 32) {
+    // ===================== copy warps: postings -> shared-memory ring =====================
+    // Every copy warp walks the same chunk sequence and issues the chunks of its own residue class.
     // Per slab the lanes look up one term's run each; the runs are then issued in term order, one
     // short serial sequence per chunk (wait for a free stage, descriptor, expect_tx, two bulk copies).
     uint32_t ps = 0, pph = 1;
+    int turn = warp - BM25_CONSUMERS / 32;      // chunks until this warp's next one
+    // returns the stage of the next chunk, or -1 when the chunk belongs to another copy warp
     auto stage_acquire = [&]() {
       const uint32_t s = ps;
-      mbar_wait(&sh.empty_bar[s], pph);
+      const uint32_t ph = pph;
       if (++ps == BM25_STAGES) { ps = 0; pph ^= 1; }
-      return s;
+      if (turn != 0) { --turn; return -1; }
+      turn = BM25_COPY_WARPS - 1;
+      mbar_wait(&sh.empty_bar[s], ph);
+      return int(s);
     };
     // control stage: no postings, just flags and two words for the consumers
-    auto emit_ctrl = [&](int flags, int z, int w) {
-      const uint32_t s = stage_acquire();
+    auto emit_ctrl = [&](int flags, int y, int z, float w) {
+      const int s = stage_acquire();
+      if (s < 0) return;
       if (lane == 0) {
-        sh.sdesc[s] = make_int4(0, flags << 8, z, w);
+        sh.sdesc[s] = make_int4(flags << 16, y, z, __float_as_int(w));
         mbar_arrive(&sh.full_bar[s]);
       }
       __syncwarp();
@@ -366,7 +394,8 @@ bm25_scan_kernel(const Bm25Params p) {
     // postings [first, first + n) -> one stage.  The copy window is widened to 16-byte units; the
     // consumers ignore what lies outside [skip, skip + n).
     auto emit = [&](int64_t first, int n, float mult, int sl0, int flags) {
-      const uint32_t s = stage_acquire();
+      const int s = stage_acquire();
+      if (s < 0) return;
       const int skip = int(first & 3);
       const int64_t a0 = first - skip;
       int cnt4 = (n + skip + 3) & ~3;
@@ -383,7 +412,7 @@ bm25_scan_kernel(const Bm25Params p) {
         __syncwarp();
       }
       if (lane == 0) {
-        sh.sdesc[s] = make_int4(n, skip | (flags << 8), __float_as_int(mult), sl0);
+        sh.sdesc[s] = make_int4(n | (skip << 12) | (flags << 16), __float_as_int(mult), sl0, 0);
         mbar_arrive_expect_tx(&sh.full_bar[s], uint32_t(cnt4) * 8u);
         if (cnt4 > 0) {
           bulk_copy_g2s(dst_id, p.doc_id + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
@@ -396,15 +425,15 @@ bm25_scan_kernel(const Bm25Params p) {
       const uint32_t bb = gc & 1;
       mbar_wait(&sh.bfull_bar[bb], (gc >> 1) & 1);
       const Bm25Group& G = sh.grp[bb];
-      if (G.kind != 0) { emit_ctrl(BM25_F_END, 0, 0); break; }
+      if (G.kind != 0) { emit_ctrl(BM25_F_END, 0, 0, 0.f); break; }
       const int nt = G.nt, ns = G.ns, chain = G.chain, step = G.step;
-      if (G.first) emit_ctrl(BM25_F_ITEM_BEGIN, step, chain);
+      if (G.first) emit_ctrl(BM25_F_ITEM_BEGIN, step, chain, G.inv_scale);
       for (int j = 0; j < ns; ++j) {
         const int sl0 = G.b0 + j * BM25_SLAB;
         const int last_t = G.last_t[j];
         if (last_t < 0) {
           // no postings here; with negative impacts a slab of zero scores still has to be ranked
-          if (!p.nonneg) emit_ctrl(BM25_F_SLAB_END | BM25_F_TERM_END, 0, sl0);
+          if (!p.nonneg) emit_ctrl(BM25_F_SLAB_END, 0, sl0, 0.f);
           continue;
         }
         for (int t0 = 0; t0 <= last_t; t0 += 32) {
@@ -423,7 +452,7 @@ bm25_scan_kernel(const Bm25Params p) {
             int64_t pos = __shfl_sync(0xffffffffu, first, src);
             int rem = __shfl_sync(0xffffffffu, cnt, src);
             const float m = __shfl_sync(0xffffffffu, mult, src);
-            const int endflags = BM25_F_TERM_END | ((t0 + src == last_t) ? BM25_F_SLAB_END : 0);
+            const int endflags = (t0 + src == last_t) ? BM25_F_SLAB_END : 0;
             while (rem > 0) {
               const int n = min(rem, BM25_CHUNK - int(pos & 3));
               emit(pos, n, m, sl0, n == rem ? endflags : 0);
@@ -433,25 +462,30 @@ bm25_scan_kernel(const Bm25Params p) {
           }
         }
       }
-      if (G.last) emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain);
+      if (G.last) emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain, 0.f);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);
     }
   } else {
     // ===================== consumers =====================
-    float mx = -INFINITY;     // largest score this thread wrote into the current slab
+    // Scores are accumulated in fixed point (int32, per-query power-of-two scale) with shared-memory
+    // integer atomics: adds commute exactly, so the terms of a slab need no ordering between them,
+    // results do not depend on which warp ran first, and one ATOMS replaces a load / add / store.
+    int mx = INT_MIN;         // largest score this thread wrote into the current slab
+    float inv_scale = 1.f;    // fixed point -> fp32 score of the current item's query
     int64_t range_end = 0;    // docs at or past the end of the chain's split are not ranked
+    int* acci = reinterpret_cast<int*>(acc);
     const uint32_t acc_u32 = smem_u32(acc);
     const uint32_t rid0 = smem_u32(ring_id) + tid * 4, rim0 = smem_u32(ring_imp) + tid * 4;
     uint32_t s = 0, ph = 0;
     for (;;) {
       mbar_wait(&sh.full_bar[s], ph);
       const int4 de = sh.sdesc[s];
-      const int n = de.x, flags = de.y >> 8, sl0 = de.w;
-      const float mult = __int_as_float(de.z);
+      const int n = de.x & 0xfff, flags = de.x >> 16, sl0 = de.z;
+      const float ms = __int_as_float(de.y);                      // term multiplicity x scale
       const uint32_t accb = acc_u32 - 4u * uint32_t(sl0);        // accb + 4 * doc == &acc[doc - slab0]
       const uint32_t rid = rid0 + s * (BM25_CHUNK * 4), rim = rim0 + s * (BM25_CHUNK * 4);
-      int d[BM25_PER_THREAD]; float v[BM25_PER_THREAD], a[BM25_PER_THREAD];
+      int d[BM25_PER_THREAD]; float v[BM25_PER_THREAD];
       if (n == BM25_CHUNK) {
         // whole stage: no predicates.  The stage is handed back as soon as it is in registers.
 #pragma unroll
@@ -459,15 +493,12 @@ bm25_scan_kernel(const Bm25Params p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
 #pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) a[u] = lds_f32(accb + 4u * uint32_t(d[u]));
-#pragma unroll
         for (int u = 0; u < BM25_PER_THREAD; ++u) {
-          a[u] = fmaf(mult, v[u], a[u]);
-          sts_f32(accb + 4u * uint32_t(d[u]), a[u]);
-          mx = fmaxf(mx, a[u]);
+          const int vi = __float2int_rn(v[u] * ms);
+          mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[u]), vi) + vi);
         }
       } else {
-        const int skip = de.y & 0xff;
+        const int skip = (de.x >> 12) & 3;
 #pragma unroll
         for (int u = 0; u < BM25_PER_THREAD; ++u) {
           const bool ok = tid + u * BM25_CONSUMERS < n;
@@ -477,10 +508,11 @@ bm25_scan_kernel(const Bm25Params p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
 #pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) a[u] = (d[u] >= 0) ? lds_f32(accb + 4u * uint32_t(d[u])) : 0.f;
-#pragma unroll
         for (int u = 0; u < BM25_PER_THREAD; ++u)
-          if (d[u] >= 0) { a[u] = fmaf(mult, v[u], a[u]); sts_f32(accb + 4u * uint32_t(d[u]), a[u]); mx = fmaxf(mx, a[u]); }
+          if (d[u] >= 0) {
+            const int vi = __float2int_rn(v[u] * ms);
+            mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[u]), vi) + vi);
+          }
       }
       if (++s == BM25_STAGES) { s = 0; ph ^= 1; }
       if (flags == 0) continue;
@@ -492,16 +524,17 @@ bm25_scan_kernel(const Bm25Params p) {
         // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
         const float thr_s = !thr_key ? -INFINITY
                             : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
-        // closes the slab's last term; with negative impacts an untouched doc (score 0) can be a hit too
-        const bool hit = consumers_bar_or(!p.nonneg || mx >= thr_s);
+        // every add of the slab is done behind this barrier; with negative impacts an untouched doc
+        // (score 0) can be a hit too
+        const bool hit = consumers_bar_or(!p.nonneg || float(mx) * inv_scale >= thr_s);
         if (hit) {
           // ---- scan the slab for candidates ----
-          const float4* a4 = reinterpret_cast<const float4*>(acc);
+          const int4* a4 = reinterpret_cast<const int4*>(acc);
 #pragma unroll 2
           for (int i = 0; i < BM25_SLAB / 4 / BM25_CONSUMERS; ++i) {
             const int idx = (tid + i * BM25_CONSUMERS) * 4;
-            const float4 s4 = a4[tid + i * BM25_CONSUMERS];
-            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            const int4 s4 = a4[tid + i * BM25_CONSUMERS];
+            const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
             const bool any4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3])) >= thr_s;
             if (!__any_sync(0xffffffffu, any4)) continue;
 #pragma unroll
@@ -516,7 +549,7 @@ bm25_scan_kernel(const Bm25Params p) {
           cbar();
           if (sh.cand_cnt > cap) {
             // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
-            Bm25Union uni{cand, cnt_before, acc, slab0, range_end, thr_key};
+            Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key};
             const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
             uint64_t keep[4];     // cap <= 4 * BM25_CONSUMERS: at most 4 old keys per thread
 #pragma unroll
@@ -536,7 +569,7 @@ bm25_scan_kernel(const Bm25Params p) {
               const int64_t doc = slab0 + i;
               uint64_t key = 0;
               bool want = doc < range_end;
-              if (want) { key = make_key(acc[i], uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
+              if (want) { key = make_key(float(acci[i]) * inv_scale, uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
               cand_append(want, key, cand, cap, &sh.cand_cnt);
             }
             cbar();
@@ -548,15 +581,14 @@ bm25_scan_kernel(const Bm25Params p) {
         float4* z4 = reinterpret_cast<float4*>(acc);
 #pragma unroll
         for (int i = 0; i < BM25_SLAB / 4 / BM25_CONSUMERS; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mx = -INFINITY;
+        mx = INT_MIN;
         cbar();
-      } else if (flags & BM25_F_TERM_END) {
-        cbar();   // the next term may touch the docs this one did
       }
 
       if (flags & BM25_F_ITEM_BEGIN) {
         // the previous item ended behind a barrier: the candidate buffer is free
-        const int chain = de.w, step = de.z;
+        const int chain = de.z, step = de.y;
+        inv_scale = __int_as_float(de.w);
         const int split = chain % p.S;
         range_end = min(p.N, int64_t(split + 1) * p.dps);
         if (step == 0) {
@@ -571,7 +603,7 @@ bm25_scan_kernel(const Bm25Params p) {
         cbar();
       }
       if (flags & BM25_F_ITEM_END) {
-        const int chain = de.w, step = de.z;
+        const int chain = de.z, step = de.y;
         if (flags & BM25_F_FINAL) {
           // ---- sorted top-k of the surviving candidates -> this chain's key list ----
           const int ncand = min(sh.cand_cnt, cap);
@@ -651,7 +683,7 @@ struct Bm25Plan {
   int64_t dps;
   unsigned long long total_items;
   size_t smem, ws;
-  size_t off[12];
+  size_t off[13];
 };
 
 static int g_item_slabs = 0;     // 0 = not yet initialised
@@ -700,6 +732,7 @@ static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int
   take(9, size_t(pl.nc) * 4);                         // ch_cnt
   take(10, pl.steps > 1 ? size_t(pl.nc) * pl.cap * 8 : 8);   // ch_cand
   take(11, size_t(pl.nc) * k * 8);                    // out_keys
+  take(12, size_t(nq) * 4);                           // q_inv_scale
   pl.ws = o;
   return pl;
 }
@@ -721,8 +754,8 @@ extern "C" size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64
 
 extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
                               const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
-                              int64_t N, int k, int64_t id_base, int nonneg, float* out_score, int64_t* out_id,
-                              void* ws, size_t ws_bytes, lrag_stream_t stream_) {
+                              int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
+                              int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && k > 0 && k <= LRAG_MAX_K, "bm25_topk: need nq > 0 and 1 <= k <= %d (nq=%d k=%d)", LRAG_MAX_K, nq, k);
@@ -732,6 +765,7 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
                "bm25_topk: a query has %lld terms; at most %d are supported", (long long)max_query_terms,
                LRAG_BM25_MAX_QUERY_TERMS);
   LRAG_REQUIRE(indptr && q_indptr && out_score && out_id, "bm25_topk: null pointer");
+  LRAG_REQUIRE(impact_bound >= 0.f && impact_bound < 3.0e38f, "bm25_topk: impact_bound must be a finite value >= max |impact|");
   LRAG_REQUIRE((reinterpret_cast<uintptr_t>(doc_id) & 15) == 0 && (reinterpret_cast<uintptr_t>(impact) & 15) == 0,
                "bm25_topk: doc_id and impact must be 16-byte aligned (bulk async copies)");
   const int sms = sm_count();
@@ -755,6 +789,8 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   p.ws.ch_cnt = reinterpret_cast<int*>(w + pl.off[9]);
   p.ws.ch_cand = reinterpret_cast<uint64_t*>(w + pl.off[10]);
   p.ws.out_keys = reinterpret_cast<uint64_t*>(w + pl.off[11]);
+  p.ws.q_inv_scale = reinterpret_cast<float*>(w + pl.off[12]);
+  p.impact_bound = impact_bound;
 
   static size_t smem_set = 0;
   if (pl.smem > smem_set) {

@@ -115,6 +115,11 @@ class Bm25DeviceIndex:
     n_docs: int
     nonneg: bool
     id_base: int = 0
+    impact_bound: float = -1.0  # >= max |impact| (sizes the fixed-point accumulators); computed when not given
+
+    def __post_init__(self):
+        if self.impact_bound < 0:
+            self.impact_bound = float(self.impact.abs().max().item()) if self.impact.numel() else 0.0
 
     @property
     def vocab(self) -> int:
@@ -143,7 +148,7 @@ def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tens
     ws = _ws(lib.lrag_bm25_topk_workspace_bytes(index.n_docs, nq, k, max_query_terms), dev)
     rc = lib.lrag_bm25_topk(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, index.nnz, _ptr(q_indptr),
                             _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
-                            _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+                            index.impact_bound, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
     check(rc, "lrag_bm25_topk")
     return s, i
 
