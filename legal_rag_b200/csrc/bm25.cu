@@ -48,17 +48,18 @@
 namespace lrag {
 
 constexpr int BM25_CONSUMERS = 512;                  // 16 warps
-constexpr int BM25_COPY_WARPS = 2;                   // chunk c is issued by copy warp c % BM25_COPY_WARPS
+constexpr int BM25_COPY_WARPS = 3;                   // chunk c is issued by copy warp c % BM25_COPY_WARPS; must not exceed BM25_STAGES (phase parity)
 constexpr int BM25_THREADS = BM25_CONSUMERS + 32 * BM25_COPY_WARPS + 32;   // consumers, copy warps, bounds warp
-constexpr int BM25_SLAB = 16384;
+constexpr int BM25_SLAB = 12288;
 constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (fewer when a query has many terms)
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
 constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
-constexpr int BM25_CHUNK = 1024;                     // postings per ring stage
+constexpr int BM25_CHUNK = 2048;                     // postings per ring stage
 constexpr int BM25_STAGES = 3;                       // 64 KB slab + 24 KB ring + 8 KB candidates + state: two CTAs per SM
 constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
+static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
 constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
 enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
 
@@ -699,7 +700,7 @@ static int bm25_item_slabs() {
 static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int sms) {
   Bm25Plan pl;
   pl.P = next_pow2(k);
-  pl.cap = 2 * pl.P < 1024 ? 1024 : 2 * pl.P;        // <= 2048 = 4 * BM25_CONSUMERS
+  pl.cap = 2 * pl.P < 512 ? 512 : 2 * pl.P;         // <= 2048 = 4 * BM25_CONSUMERS
   pl.TS = int(max_query_terms < 1 ? 1 : (max_query_terms > BM25_MAXT ? BM25_MAXT : max_query_terms));
   pl.item_slabs = bm25_item_slabs();
   const int64_t item_docs = int64_t(pl.item_slabs) * BM25_SLAB;
