@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|bm25|fuse]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|bm25|hybrid]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
@@ -305,7 +305,131 @@ class Bm25Workload:
     cpu_cores = 1
 
 
-WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "bm25": Bm25Workload}
+class HybridWorkload:
+    """BASELINE.json configs[4]: full hybrid (dense 100M x 768 + BM25 + ColBERT rerank + weighted fusion) sharded over the
+    GPUs of one box with NCCL top-k merges.  Weak scaling: every rank owns 1/8 of the config's stores (12.5M x 768 dense rows,
+    12.5M BM25 docs of mean length 24, 125k x 128 x 128 token rows), so 8 ranks hold exactly configs[4]."""
+    name = "hybrid_top100"
+    dtype = "bf16"
+    dominant = "dense_scan"
+
+    def __init__(self, args, rank, world, device):
+        self.N, self.d, self.V = args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
+        self.nq, self.k, self.kc = args.nq or 4096, args.k, args.k
+        self.Nd_tok, self.Ld, self.Lq = max(1, self.N // 100), 128, 32
+        self.rank, self.world, self.device = rank, world, device
+
+    def config(self):
+        return {"workload": f"configs[4] hybrid top-{self.k}: per GPU {self.N} x {self.d} bf16 dense rows + {self.N} BM25 docs (Zipf vocab {self.V}, "
+                            f"mean length 24) + {self.Nd_tok} x {self.Ld} x 128 ColBERT token rows; batch {self.nq} queries; per-channel top-{self.kc}, "
+                            f"MaxSim over the fused candidate union (<= {2 * self.kc}), weighted_sum 0.6/0.4/0.35",
+                "corpus_docs_total": self.N * self.world, "postings": getattr(self, "nnz", None),
+                "token_rows": "global id mod total token rows (synthetic aliasing of the id space onto the token store, SURVEY 8d C5)",
+                "parallelism": (f"doc-sharded x{self.world}: per channel local top-k + NCCL all-gather + merge, MaxSim by row owner + NCCL max-reduce, "
+                                f"replicated fusion") if self.world > 1 else "single GPU",
+                "l2": f"dense shard {self.N * self.d * 2 / 1e9:.1f} GB >> 126 MB L2",
+                "stages_ms": getattr(self, "stages_ms", None),
+                "value_definition": "value = n_gpus * batch_queries * steps / time (every rank answers the whole batch against its shard)"}
+
+    def setup(self):
+        import torch
+        from legal_rag_b200 import engine, synth
+        self.torch, self.engine = torch, engine
+        base = self.rank * self.N
+        X = synth.unit_rows_bf16(self.N, self.d, 20 + self.rank, self.device)
+        index, st = synth.bm25_synthetic_index(self.N, self.V, 10 + self.rank, self.device, mean_len=24.0, id_base=base)
+        self.nnz = st["nnz"]
+        tokens = synth.unit_tokens_bf16(self.Nd_tok, self.Ld, 128, 5 + self.rank, self.device)
+        self.shard = engine.HybridShard(X, index, tokens, None, id_base=base, tok_row_base=self.rank * self.Nd_tok,
+                                        tok_rows_total=self.Nd_tok * self.world)
+        self.Qd = synth.unit_rows_bf16(self.nq, self.d, 21, self.device, chunk=self.nq)
+        self.q_indptr, self.q_term, self.mx = synth.bm25_synthetic_queries(self.nq, self.V, 11, self.device)
+        self.Qtok = synth.unit_tokens_bf16(self.nq, self.Lq, 128, 7, self.device)
+        self.host = [t.cpu().pin_memory() for t in (self.Qd, self.q_indptr, self.q_term, self.Qtok)]
+        self._stage_times()
+
+    def _stage_times(self):
+        """Per-stage device times of one step (outside the timed region), reported in config.stages_ms."""
+        torch, eng, sh = self.torch, self.engine, self.shard
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            marks = [ev() for _ in range(5)]
+            marks[0].record()
+            d = eng.allgather_merge(*eng.dense_topk(sh.X, self.Qd, self.kc, sh.id_base), self.kc)
+            marks[1].record()
+            b = eng.allgather_merge(*eng.bm25_topk(sh.bm25, self.q_indptr, self.q_term, self.mx, self.kc), self.kc)
+            marks[2].record()
+            _, gid = eng.fuse_topk(d, b, None, k=2 * self.kc, method="weighted_sum")
+            rows = torch.where(gid >= 0, gid % sh.tok_rows_total, gid) - sh.tok_row_base
+            own = (gid >= 0) & (rows >= 0) & (rows < sh.tokens.shape[0])
+            eng.maxsim_scores(sh.tokens, None, self.Qtok, torch.where(own, rows, torch.full_like(rows, -1)))
+            marks[3].record()
+            self.step()
+            marks[4].record()
+            torch.cuda.synchronize()
+        self.stages_ms = {"dense+merge": marks[0].elapsed_time(marks[1]), "bm25+merge": marks[1].elapsed_time(marks[2]),
+                          "candidates+maxsim": marks[2].elapsed_time(marks[3]), "whole_step": marks[3].elapsed_time(marks[4])}
+
+    def step(self):
+        return self.shard.search_device(self.Qd, self.q_indptr, self.q_term, self.mx, self.Qtok, k=self.k, kc=self.kc)
+
+    def e2e_step(self):
+        return self.shard.search(self.host[0], self.host[1], self.host[2], self.mx, self.host[3], k=self.k, kc=self.kc)
+
+    def e2e_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host), self.nq * self.k * 12
+
+    def units_per_step(self):
+        return self.nq * self.world
+
+    def roofline(self, kernel_ms, peaks):
+        flops = 2.0 * self.nq * self.N * self.d
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "traffic": None, "kernel": "dense_scan_kernel (dominant stage of the hybrid step)", "kernel_ms": kernel_ms,
+                "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per step", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+
+    def cpu_sample(self, budget_s=15.0):
+        """The reference's sequential path (hybrid_retriever.py:282-384) restated: flat-IP + literal BM25 + MaxSim of the
+        candidate union + _fuse, single query at a time, on a 20k-doc sample; dense and BM25 extrapolated linearly in docs."""
+        import numpy as np
+        from oracle import bm25 as obm25, dense as odense, fuse as ofuse, maxsim as omaxsim
+        n_s, v_s, nq_s = 20_000, 5_000, 4
+        rng = np.random.default_rng(20)
+        X = rng.standard_normal((n_s, self.d), dtype=np.float32); X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q = rng.standard_normal((nq_s, self.d), dtype=np.float32); Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+        p = 1.0 / np.arange(1, v_s + 1); p /= p.sum()
+        lens = np.clip(np.round(rng.lognormal(np.log(24), 0.6, n_s)), 4, 512).astype(np.int64)
+        flat = rng.choice(v_s, size=int(lens.sum()), p=p)
+        off = np.concatenate([[0], np.cumsum(lens)])
+        lit = obm25.BM25Okapi([[str(t) for t in flat[off[i]:off[i + 1]]] for i in range(n_s)])
+        queries = [[str(t) for t in rng.choice(v_s, size=int(rng.integers(2, 9)), p=p)] for _ in range(nq_s)]
+        D = rng.standard_normal((2000, self.Ld, 128), dtype=np.float32)
+        Qt = rng.standard_normal((nq_s, self.Lq, 128), dtype=np.float32)
+
+        def run():
+            t_scan = t_rest = 0.0
+            for j in range(nq_s):
+                t0 = time.perf_counter()
+                ds, di = odense.flat_ip_topk(Q[j:j + 1], X, self.kc)
+                bs, bi = obm25.search(lit, queries[j], self.kc)
+                t1 = time.perf_counter()
+                dl = list(zip(di[0].tolist(), ds[0].tolist())); bl = list(zip(bi.tolist(), bs.tolist()))
+                cand = np.array([[r["id"] % 2000 for r in ofuse.fuse(dl, bl, [], method="weighted_sum")]])
+                cs = omaxsim.maxsim_scores(Qt[j:j + 1], D, None, cand)[0]
+                order = np.argsort(-cs, kind="stable")[:self.kc]
+                ofuse.fuse(dl, bl, [(int(cand[0][o]), float(cs[o])) for o in order], method="weighted_sum")
+                t2 = time.perf_counter()
+                t_scan += t1 - t0; t_rest += t2 - t1
+            dt = t_scan * self.N / n_s + t_rest
+            return nq_s / dt, t_scan + t_rest
+        return run, (f"oracle restatement of the reference's sequential hybrid path, one query at a time: numpy flat-IP + literal BM25Okapi over "
+                     f"{n_s} docs (extrapolated linearly to {self.N}), MaxSim of the candidate union, _fuse; {nq_s} queries per step")
+
+    cpu_cores = 1
+
+
+WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "bm25": Bm25Workload, "hybrid": HybridWorkload}
 
 
 # =================================================================================================

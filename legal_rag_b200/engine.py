@@ -287,6 +287,55 @@ def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None,
     return (merge or topk_merge)(cat_s, cat_i, k)
 
 
+@dataclass
+class HybridShard:
+    """One rank's slice of the three stores plus the batched hybrid search over them:
+
+        dense local top-kc  -> all-gather + merge  \
+        BM25  local top-kc  -> all-gather + merge   > candidates = fused union (<= 2 kc per query)
+        MaxSim of the candidates whose token rows this rank owns -> max-reduce over ranks -> ColBERT list
+        three-channel fusion (HybridRetriever._fuse, hybrid_retriever.py:389-551) -> top-k
+
+    Fusion runs on the merged lists only: min-max bounds and RRF ranks are properties of the global
+    per-channel list.  `tok_rows_total` maps a global doc id to a token-store row (id mod rows): the
+    synthetic configs alias a 10^8-id space onto a 10^6-doc token store, real corpora use rows == docs."""
+    X: torch.Tensor                          # [N_local, d] bf16
+    bm25: Bm25DeviceIndex                    # id_base == dense id_base
+    tokens: Optional[torch.Tensor] = None    # [Nd_local, Ld, 128] bf16
+    doclen: Optional[torch.Tensor] = None
+    id_base: int = 0
+    tok_row_base: int = 0
+    tok_rows_total: int = 0
+    group: object = None
+
+    def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
+                      Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",
+                      w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, **fuse_kw):
+        import torch.distributed as dist
+        ds, di = allgather_merge(*dense_topk(self.X, Qd, kc, self.id_base), kc, self.group)
+        bs, bi = allgather_merge(*bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc), kc, self.group)
+        kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, w_colbert=w_colbert, **fuse_kw)
+        if self.tokens is None or Qtok is None:
+            return fuse_topk((ds, di), (bs, bi), None, k=k, **kw)
+        # candidate set = every doc either channel returned, best fused first; -1 pads short rows
+        _, cand_gid = fuse_topk((ds, di), (bs, bi), None, k=2 * kc, method=method, w_dense=w_dense, w_bm25=w_bm25)
+        rows = torch.where(cand_gid >= 0, cand_gid % max(1, self.tok_rows_total), cand_gid) - self.tok_row_base
+        owned = (cand_gid >= 0) & (rows >= 0) & (rows < self.tokens.shape[0])
+        cs = maxsim_scores(self.tokens, self.doclen, Qtok, torch.where(owned, rows, torch.full_like(rows, -1)))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(cs, op=dist.ReduceOp.MAX, group=self.group)      # every candidate has exactly one owner
+        cs = torch.where(cs == float("-inf"), torch.full_like(cs, PAD_SCORE), cs)
+        cls, cli = topk_select(cs, min(kc, cs.shape[1]), col_id=cand_gid)
+        return fuse_topk((ds, di), (bs, bi), (cls, cli), k=k, **kw)
+
+    def search(self, Qd_host, qi_host, qt_host, max_query_terms: int, Qtok_host, k: int = 100, **kw):
+        """Host (pinned) inputs -> H2D -> search_device -> D2H; returns CPU (scores [nq, k], ids [nq, k])."""
+        dev = self.X.device
+        up = lambda t: None if t is None else t.to(dev, non_blocking=True)
+        s, i = self.search_device(up(Qd_host), up(qi_host), up(qt_host), max_query_terms, up(Qtok_host), k=k, **kw)
+        return s.cpu(), i.cpu()
+
+
 class FlatIPShard:
     """Device-resident bf16 corpus shard [N, d] with the faiss-shaped batched search entry point:
     search(Q) with Q on the HOST (pinned) does H2D -> scan -> (all-gather merge) -> D2H."""

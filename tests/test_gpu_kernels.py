@@ -384,3 +384,39 @@ def test_bm25_device_built_scale_model_matches_oracle(eng):
     qi, qt = qi.cpu().numpy(), qt.cpu().numpy()
     O = [csr.search(qt[qi[j]:qi[j + 1]].tolist(), 150) for j in range(256)]
     check_topk_parity(s, i, np.stack([o[0] for o in O]), np.stack([o[1] for o in O]), 100, TAU_FP32, what="bm25-scale-model")
+
+
+# ---------------------------------------------------------------- batched hybrid pipeline (one shard)
+def test_hybrid_shard_matches_oracle_pipeline(eng):
+    """engine.HybridShard on one GPU: per-channel top-kc -> candidate union -> MaxSim -> three-channel fusion,
+    against the same pipeline assembled from the oracle pieces."""
+    from legal_rag_b200.bm25_index import Bm25HostIndex
+    from oracle import maxsim as omaxsim
+    rng = np.random.default_rng(77)
+    N, d, V, nq, Ld, Lq, kc, k = 4000, 128, 800, 12, 32, 8, 20, 10
+    Xd, Xr = _bf16(_unit(rng, (N, d)))
+    Qd, Qr = _bf16(_unit(rng, (nq, d)))
+    docs = [rng.integers(0, V, int(rng.integers(5, 30))) for _ in range(N)]
+    host = Bm25HostIndex.from_token_ids(docs, V)
+    csr = obm25.CsrBM25.from_token_ids(docs, V)
+    queries = [rng.integers(0, V, int(rng.integers(2, 6))).tolist() for _ in range(nq)]
+    qi, qt, mx = host.encode_queries(queries)
+    Td, Tr = _bf16(_unit(rng, (N, Ld, 128)))
+    Qtd, Qtr = _bf16(_unit(rng, (nq, Lq, 128)))
+    shard = eng.HybridShard(Xd, host.to_device("cuda"), Td, None, id_base=0, tok_row_base=0, tok_rows_total=N)
+    for method in ("weighted_sum", "rrf_norm_blend"):
+        s, i = shard.search_device(Qd, torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), mx, Qtd, k=k, kc=kc, method=method)
+        s, i = s.cpu().numpy(), i.cpu().numpy()
+        D, I = odense.flat_ip_topk(Qr, Xr, kc)
+        for q in range(nq):
+            dl = list(zip(I[q].tolist(), D[q].tolist()))
+            bs, bi = csr.search(queries[q], kc)
+            bl = list(zip(bi.tolist(), bs.tolist()))
+            cand = np.array([[r["id"] for r in ofuse.fuse(dl, bl, [], method=method)]])
+            cs = omaxsim.maxsim_scores(Qtr[q:q + 1], Tr, None, cand)[0]
+            order = np.lexsort((cand[0], -cs))[:kc]
+            cl = [(int(cand[0][o]), float(cs[o])) for o in order]
+            ref = ofuse.fuse(dl, bl, cl, method=method)
+            m = min(len(ref), k + 8)
+            check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
+                              k, 2e-3, what=f"hybrid-{method}")

@@ -4,7 +4,7 @@
 TAG=$1; KREGEX=$2; shift 2
 mkdir -p gpurun_out
 python bench.py "$@" --no-cpu-baseline > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:lrag:: -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py "$@" --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list exit $?"
 python bench.py "$@" --no-cpu-baseline > gpurun_out/plain2_$TAG.log 2>&1 &&
