@@ -236,10 +236,12 @@ class Bm25Workload:
 
     def __init__(self, args, rank, world, device):
         self.N, self.V, self.nq, self.k = args.n_docs or 50_000_000, args.vocab or 500_000, args.nq or 8192, args.k
+        self.mean_len = args.mean_len or 40.0
         self.rank, self.world, self.device = rank, world, device
 
     def config(self):
-        return {"workload": f"configs[3] BM25 top-{self.k}: {self.N} docs per GPU, Zipf(1) vocab {self.V}, {self.nq} queries of 2-8 terms",
+        return {"workload": f"configs[3] BM25 top-{self.k}: {self.N} docs per GPU (mean length {self.mean_len:g}), Zipf(1) vocab {self.V}, "
+                            f"{self.nq} queries of 2-8 terms",
                 "postings": getattr(self, "nnz", None), "avgdl": getattr(self, "avgdl", None),
                 "l2": "postings streamed per step >> 126 MB L2",
                 "parallelism": f"doc-sharded x{self.world}" if self.world > 1 else "single GPU"}
@@ -249,7 +251,8 @@ class Bm25Workload:
         import torch
         from legal_rag_b200 import engine, synth
         self.torch, self.engine = torch, engine
-        self.index, st = synth.bm25_synthetic_index(self.N, self.V, 10 + self.rank, self.device, id_base=self.rank * self.N)
+        self.index, st = synth.bm25_synthetic_index(self.N, self.V, 10 + self.rank, self.device, id_base=self.rank * self.N,
+                                                    mean_len=self.mean_len)
         self.nnz, self.avgdl = st["nnz"], st["avgdl"]
         self.q_indptr, self.q_term, self.mx = synth.bm25_synthetic_queries(self.nq, self.V, 11, self.device)
         df = st["df"].cpu().numpy()
@@ -468,6 +471,7 @@ def main():
     ap.add_argument("--vocab", type=int, default=0)
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--mean-len", type=float, default=0.0, help="bm25: mean document length of the synthetic corpus (default 40)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup

@@ -59,6 +59,7 @@ constexpr int BM25_STAGES = 3;                       // 64 KB slab + 24 KB ring 
 constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
+constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
 constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
 enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
@@ -552,9 +553,9 @@ bm25_scan_kernel(const Bm25Params p) {
             // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
             Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key};
             const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
-            uint64_t keep[4];     // cap <= 4 * BM25_CONSUMERS: at most 4 old keys per thread
+            uint64_t keep[BM25_KEEP];     // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < BM25_KEEP; ++i) {
               const int idx = tid + i * BM25_CONSUMERS;
               keep[i] = idx < cnt_before ? cand[idx] : 0ull;
             }
@@ -562,7 +563,7 @@ bm25_scan_kernel(const Bm25Params p) {
             if (tid == 0) sh.cand_cnt = 0;
             cbar();
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < BM25_KEEP; ++i) {
               const bool want = keep[i] != 0ull && keep[i] >= pivot;
               cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
             }

@@ -16,4 +16,5 @@ run() {
 }
 for s in ${1:-8}; do run $s "--n-docs 5000000 --nq 1024"; done
 for s in ${2:-8}; do run $s "--n-docs 50000000 --nq 8192"; done
+for s in ${3:-}; do run $s "--n-docs 12500000 --nq 4096 --mean-len 24"; done
 cat gpurun_out/bm25.log
