@@ -44,33 +44,103 @@ def build_bm25_index(cfg, chunks: Sequence[LawChunk], tokenizer=None) -> None:
     artifacts.write_bm25_pickle(rcfg.bm25_index_file, state, chunks)
 
 
+def _load_jsonl_chunks(path) -> List[LawChunk]:
+    path = Path(path)
+    if not path.exists():
+        raise FileNotFoundError(path)
+    chunks: List[LawChunk] = []
+    with path.open("r", encoding="utf-8") as f:
+        for line in f:
+            if line.strip():
+                chunks.append(LawChunk.model_validate(json.loads(line)))
+    return chunks
+
+
+def _file_lock(path):
+    """The reference serialises writers with filelock.FileLock (incremental_dense_builder.py:45-46)."""
+    try:
+        from filelock import FileLock
+        return FileLock(str(path))
+    except ImportError:      # single-writer deployments work without it
+        import contextlib
+        return contextlib.nullcontext()
+
+
 class IncrementalDenseBuilder:
-    """builders/incremental_dense_builder.py:31-78: append new chunks to the live index; the meta file is
-    appended BEFORE the index file is rewritten, so a reader never sees an index row without its chunk."""
+    """builders/incremental_dense_builder.py:17-78: append the chunks whose id is not indexed yet.  The meta
+    file is appended BEFORE the index file is replaced (atomically), so a reader never sees an index row
+    without its chunk; writers are serialised by a lock file next to the index."""
 
     def __init__(self, cfg, store: Optional[VectorStore] = None):
         self.cfg = cfg
         self.store = store or VectorStore.from_config(cfg)
+        self.vs = self.store          # the reference's attribute name
 
     def add_chunks(self, chunks: Sequence[LawChunk]) -> int:
         if not chunks:
             return 0
-        self.store.load()
-        vecs = self.store._embed([c.text for c in chunks], is_query=False)
-        with open(self.store.meta_path, "a", encoding="utf-8") as f:
+        lock_path = Path(self.cfg.retrieval.faiss_index_file).with_suffix(".lock")
+        with _file_lock(lock_path):
+            self.store.load()
+            exist_ids = {c.id for c in self.store.chunks}
+            new_chunks, seen = [], set()
             for c in chunks:
-                f.write(json.dumps(c.model_dump(), ensure_ascii=False) + "\n")
-        self.store.index.add(vecs)
-        self.store.chunks.extend(chunks)
-        artifacts.write_faiss_flat(self.store.index_path, self.store.index.reconstruct_n())
-        self.store._index_mtime = self.store.index_path.stat().st_mtime
-        self.store._meta_mtime = self.store.meta_path.stat().st_mtime
-        return len(chunks)
+                if c.id not in exist_ids and c.id not in seen:
+                    new_chunks.append(c)
+                    seen.add(c.id)
+            if not new_chunks:
+                return 0
+            vecs = self.store._embed([c.text for c in new_chunks], is_query=False)
+            self.store.meta_path.parent.mkdir(parents=True, exist_ok=True)
+            with open(self.store.meta_path, "a", encoding="utf-8") as f:
+                for c in new_chunks:
+                    f.write(json.dumps(c.model_dump(), ensure_ascii=False) + "\n")
+            self.store.index.add(vecs)
+            self.store.chunks.extend(new_chunks)
+            self.store.index_path.parent.mkdir(parents=True, exist_ok=True)
+            artifacts.write_faiss_flat(self.store.index_path, self.store.index.reconstruct_n())
+            self.store._index_mtime = self.store.index_path.stat().st_mtime
+            self.store._meta_mtime = self.store.meta_path.stat().st_mtime
+        return len(new_chunks)
 
     def add_jsonl(self, path) -> int:
-        chunks: List[LawChunk] = []
-        with open(path, "r", encoding="utf-8") as f:
-            for line in f:
-                if line.strip():
-                    chunks.append(LawChunk.model_validate(json.loads(line)))
-        return self.add_chunks(chunks)
+        return self.add_chunks(_load_jsonl_chunks(path))
+
+
+class IncrementalBM25Builder:
+    """builders/incremental_bm25_builder.py:19-82: BM25 statistics are global (idf, avgdl), so an increment
+    re-derives the Okapi state over existing + new chunks and replaces bm25.pkl atomically.  Chunks whose id
+    is already present are skipped; an unreadable pickle counts as empty, like the reference (:31-41)."""
+
+    def __init__(self, cfg, tokenizer=None):
+        self.cfg = cfg
+        self.tokenizer = tokenizer
+
+    def _load_existing(self) -> List[LawChunk]:
+        path = Path(self.cfg.retrieval.bm25_index_file)
+        if not path.exists():
+            return []
+        try:
+            payload = artifacts.read_bm25_pickle(path)
+            return [LawChunk.model_validate(c) for c in (payload.get("chunks") or [])]
+        except Exception:
+            return []
+
+    def add_chunks(self, chunks: Sequence[LawChunk]) -> int:
+        if not chunks:
+            return 0
+        existing = self._load_existing()
+        exist_ids = {c.id for c in existing}
+        new_chunks = [c for c in chunks if c.id not in exist_ids]
+        if not new_chunks:
+            return 0
+        all_chunks = existing + list(new_chunks)
+        tok = self.tokenizer or encoders.default_query_tokenizer()     # the reference re-tokenises with jieba.cut (:70)
+        state = artifacts.okapi_state_from_tokens([tok(c.text) for c in all_chunks])
+        path = Path(self.cfg.retrieval.bm25_index_file)
+        path.parent.mkdir(parents=True, exist_ok=True)
+        artifacts.write_bm25_pickle(path, state, all_chunks)             # tmp file + os.replace
+        return len(new_chunks)
+
+    def add_jsonl(self, path) -> int:
+        return self.add_chunks(_load_jsonl_chunks(path))

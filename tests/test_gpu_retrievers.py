@@ -158,3 +158,6 @@ def test_incremental_add_is_searchable_and_persisted(world):
     assert hits[0][0].id == "new::1"
     X, info = artifacts.read_faiss_index(cfg.retrieval.faiss_index_file)      # rewritten as a flat file, row count grown
     assert X.shape[0] == n0 + 1 and len(artifacts.read_meta_jsonl(cfg.retrieval.faiss_meta_file)) == n0 + 1
+    # ids that are already indexed are skipped (incremental_dense_builder.py:51-58)
+    assert builders.IncrementalDenseBuilder(cfg, store).add_chunks([new, new]) == 0
+    assert store.index.ntotal == n0 + 1

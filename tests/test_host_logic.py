@@ -159,3 +159,33 @@ def test_shard_ranges_cover_the_corpus():
         spans = [shard_range(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_incremental_bm25_builder_dedups_rebuilds_and_replaces_atomically(tmp_path):
+    """builders/incremental_bm25_builder.py:43-82: ids already indexed are skipped, the Okapi statistics are
+    re-derived over existing + new chunks, the pickle is replaced in one step and stays readable by the shim."""
+    from legal_rag_b200.config import AppConfig
+    from legal_rag_b200.retrieval import builders
+    cfg = AppConfig()
+    cfg.retrieval.bm25_index_file = str(tmp_path / "idx" / "bm25.pkl")
+    first = _chunks(5)
+    builders.build_bm25_index(cfg, first, tokenizer=encoders.tokenize_en)
+    inc = builders.IncrementalBM25Builder(cfg, tokenizer=encoders.tokenize_en)
+    jl = tmp_path / "new.jsonl"
+    more = _chunks(8)                       # c0..c4 are duplicates, c5..c7 are new
+    jl.write_text("\n".join(json.dumps(c.model_dump()) for c in more) + "\n\n", encoding="utf-8")
+    assert inc.add_jsonl(jl) == 3
+    assert inc.add_jsonl(jl) == 0           # nothing new the second time
+    payload = artifacts.read_bm25_pickle(cfg.retrieval.bm25_index_file)
+    assert [c["id"] for c in payload["chunks"]] == [f"c{i}" for i in range(8)]
+    ref = obm25.BM25Okapi([encoders.tokenize_en(c.text) for c in more])
+    got = payload["bm25"]
+    assert got.corpus_size == 8 and abs(got.avgdl - ref.avgdl) < 1e-12
+    assert got.idf == pytest.approx(ref.idf)
+    assert not os.path.exists(cfg.retrieval.bm25_index_file + ".tmp")
+    with pytest.raises(FileNotFoundError):
+        inc.add_jsonl(tmp_path / "missing.jsonl")
+    # an unreadable pickle counts as an empty index (incremental_bm25_builder.py:31-41)
+    with open(cfg.retrieval.bm25_index_file, "wb") as f:
+        f.write(b"not a pickle")
+    assert inc.add_chunks(_chunks(2)) == 2
