@@ -30,6 +30,20 @@ METRIC = "hybrid queries/sec @k=100 (1/2/4/8 B200); dense/MaxSim scan GB/s vs HB
 UNIT = "queries/s"
 
 
+def measured_traffic(kernel: str, **shape):
+    """DRAM bytes per step of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum over the launches of one
+    step, from one `ncu --set full` capture kept under profiles/).  Only returned when the capture was taken at exactly
+    this workload shape; otherwise null."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            entry = json.load(f).get(kernel)
+        if entry and all(entry["shape"].get(k) == v for k, v in shape.items()):
+            return entry["dram_bytes_per_step"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -134,7 +148,8 @@ class DenseWorkload:
         flops = 2.0 * self.nq * self.N * self.d
         ach = flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "traffic": None, "kernel": "dense_scan_kernel", "kernel_ms": kernel_ms,
+                "traffic": measured_traffic("dense_scan_kernel", N=self.N, d=self.d, nq=self.nq, k=self.k),
+                "kernel": "dense_scan_kernel", "kernel_ms": kernel_ms,
                 "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per launch", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
                 "scan_gbs": self.N * self.d * 2 / (kernel_ms * 1e-3) / 1e9}
 
@@ -280,7 +295,8 @@ class Bm25Workload:
     def roofline(self, kernel_ms, peaks):
         nbytes = 8.0 * self.alg_postings
         ach = nbytes / (kernel_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": measured_traffic("bm25_scan_kernel", N=self.N, V=self.V, nq=self.nq, k=self.k, mean_len=self.mean_len),
                 "kernel": "bm25_scan_kernel", "kernel_ms": kernel_ms,
                 "algorithmic": f"8 B x sum_q sum_(distinct t in q) df(t) = {nbytes:.4e} B per launch", "peak_source": peaks["source"] + " (copy bandwidth)"}
 

@@ -62,6 +62,7 @@ constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
 constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
+constexpr int BM25_GATHER_MAX = 32;                  // runs this short share one ring stage (one lane per posting)
 enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
 
 struct Bm25Ws {
@@ -128,6 +129,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_s
                    smem_u32(smem_dst)),
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// 4-byte asynchronous global -> shared copy of the executing thread, and the arrive that fires on an
+// mbarrier once all of this thread's earlier copies have landed (pending count +1 now, -1 then)
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // barrier over the consumer warps that also ORs a predicate across them
@@ -423,6 +433,34 @@ bm25_scan_kernel(const Bm25Params p) {
       }
       __syncwarp();
     };
+    // Short runs (rare terms: a handful of postings per slab) with the same multiplier share ONE
+    // stage: lane l copies posting l of each run with 4-byte asynchronous copies packed back to back,
+    // and the stage's barrier completes when every lane's copies have landed.
+    auto emit_gather = [&](uint32_t runs, int64_t first, int cnt, float mult, int sl0, int flags) {
+      const int s = stage_acquire();
+      if (s < 0) return;
+      int32_t* dst_id = ring_id + s * BM25_CHUNK;
+      float* dst_imp = ring_imp + s * BM25_CHUNK;
+      int total = 0;
+      while (runs) {
+        const int src = __ffs(runs) - 1;
+        runs &= runs - 1;
+        const int64_t f = __shfl_sync(0xffffffffu, first, src);
+        const int c = __shfl_sync(0xffffffffu, cnt, src);
+        if (lane < c) {
+          cp_async_4(dst_id + total + lane, p.doc_id + f + lane);
+          cp_async_4(dst_imp + total + lane, p.impact + f + lane);
+        }
+        total += c;
+      }
+      cp_async_mbar_arrive(&sh.full_bar[s]);
+      __syncwarp();
+      if (lane == 0) {
+        sh.sdesc[s] = make_int4(total | (flags << 16), __float_as_int(mult), sl0, 0);
+        mbar_arrive(&sh.full_bar[s]);
+      }
+      __syncwarp();
+    };
     for (uint32_t gc = 0;; ++gc) {
       const uint32_t bb = gc & 1;
       mbar_wait(&sh.bfull_bar[bb], (gc >> 1) & 1);
@@ -448,13 +486,26 @@ bm25_scan_kernel(const Bm25Params p) {
             mult = G.t_mult[t];
           }
           uint32_t live = __ballot_sync(0xffffffffu, cnt > 0);
+          // short runs of a (single-batch) slab that share a multiplier travel together
+          uint32_t shorts = 0;
+          float short_mult = 0.f;
+          if (last_t < 32) {
+            const uint32_t cand_short = __ballot_sync(0xffffffffu, cnt > 0 && cnt <= BM25_GATHER_MAX);
+            if (__popc(cand_short) >= 2) {
+              short_mult = __shfl_sync(0xffffffffu, mult, __ffs(cand_short) - 1);
+              shorts = __ballot_sync(0xffffffffu, cnt > 0 && cnt <= BM25_GATHER_MAX && mult == short_mult);
+              if (__popc(shorts) < 2) shorts = 0;
+            }
+          }
+          live &= ~shorts;
+          const int last_run = shorts ? -1 : (last_t < 32 ? 31 - __clz(int(live)) : last_t);   // run that ends the slab
           while (live) {
             const int src = __ffs(live) - 1;
             live &= live - 1;
             int64_t pos = __shfl_sync(0xffffffffu, first, src);
             int rem = __shfl_sync(0xffffffffu, cnt, src);
             const float m = __shfl_sync(0xffffffffu, mult, src);
-            const int endflags = (t0 + src == last_t) ? BM25_F_SLAB_END : 0;
+            const int endflags = (t0 + src == last_run) ? BM25_F_SLAB_END : 0;
             while (rem > 0) {
               const int n = min(rem, BM25_CHUNK - int(pos & 3));
               emit(pos, n, m, sl0, n == rem ? endflags : 0);
@@ -462,6 +513,7 @@ bm25_scan_kernel(const Bm25Params p) {
               rem -= n;
             }
           }
+          if (shorts) emit_gather(shorts, first, cnt, short_mult, sl0, BM25_F_SLAB_END);
         }
       }
       if (G.last) emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain, 0.f);
@@ -498,6 +550,18 @@ bm25_scan_kernel(const Bm25Params p) {
         for (int u = 0; u < BM25_PER_THREAD; ++u) {
           const int vi = __float2int_rn(v[u] * ms);
           mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[u]), vi) + vi);
+        }
+      } else if (n <= BM25_CONSUMERS) {
+        // short run (the usual partial stage): at most one posting per thread, and warps past the
+        // end of the run only hand the stage back
+        const int skip = (de.x >> 12) & 3;
+        const bool ok = tid < n;
+        if (ok) { d[0] = lds_s32(rid + skip * 4); v[0] = lds_f32(rim + skip * 4); }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
+        if (ok) {
+          const int vi = __float2int_rn(v[0] * ms);
+          mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[0]), vi) + vi);
         }
       } else {
         const int skip = (de.x >> 12) & 3;
