@@ -46,7 +46,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     procs = []
     for src in SOURCES:
         obj = objdir / (src[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("LRAG_NVCC_EXTRA", "").split(), "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

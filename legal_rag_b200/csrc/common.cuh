@@ -130,6 +130,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same, polling without the suspend hint.  Which flavour wins is measured per kernel
+// (tools/gpu_wait_ab.sh): the dense scan gains 7 % from parked waits (its epilogue warps wait long and
+// would otherwise take issue slots from the TMA / MMA warps), the MaxSim gather loses 13 % to the wake-up
+// latency (its waits are short and frequent), so maxsim.cu polls.
+__device__ __forceinline__ bool mbar_try_wait_now(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_now(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_now(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) {
+      printf("lrag: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
                                             int32_t c0, int32_t c1) {
   asm volatile(

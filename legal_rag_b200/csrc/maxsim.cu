@@ -85,7 +85,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (row < 0 || row >= p.Nd) row = 0;   // skipped slot: keep the pipeline uniform, result is discarded
       const uint32_t ab = itc & 1;
       if (lane == 0) {
-        mbar_wait(&aempty_bar[ab], ((itc >> 1) & 1) ^ 1);
+        mbar_wait_spin(&aempty_bar[ab], ((itc >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&afull_bar[ab], MS_A_BYTES);
         uint8_t* a = a_buf + ab * MS_A_BYTES;
 #pragma unroll
@@ -98,7 +98,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int64_t rw = __shfl_sync(0xffffffffu, row, c);
         if (lane == 0) {
           const uint32_t s = n % NS, use = n / NS;
-          mbar_wait(&empty_bar[s], (use & 1) ^ 1);
+          mbar_wait_spin(&empty_bar[s], (use & 1) ^ 1);
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
           uint8_t* b = b_buf + size_t(s) * stage_bytes;
           tma_load_2d(b, &tmap_d, &full_bar[s], 0, int32_t(rw * p.Ld));
@@ -115,12 +115,12 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int c0 = int(it % p.chunks) * MS_CHUNK;
         const int nc = min(MS_CHUNK, p.C - c0);
         const uint32_t ab = itc & 1;
-        mbar_wait(&afull_bar[ab], (itc >> 1) & 1);
+        mbar_wait_spin(&afull_bar[ab], (itc >> 1) & 1);
         const uint32_t a_addr = smem_u32(a_buf + ab * MS_A_BYTES);
         for (int c = 0; c < nc; ++c, ++n) {
           const uint32_t s = n % NS, use = n / NS;
-          mbar_wait(&tempty_bar[s], (use & 1) ^ 1);
-          mbar_wait(&full_bar[s], use & 1);
+          mbar_wait_spin(&tempty_bar[s], (use & 1) ^ 1);
+          mbar_wait_spin(&full_bar[s], use & 1);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_buf + size_t(s) * stage_bytes);
           const uint32_t tmem_d = tmem_base + s * p.col_stride;
@@ -155,7 +155,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           const int64_t row = p.cand[size_t(q) * p.C + c0 + c];
           const bool skip = row < 0 || row >= p.Nd;
           const int dl = skip ? 0 : (p.doclen ? min(p.doclen[row], p.Ld) : p.Ld);
-          mbar_wait(&tfull_bar[e], use & 1);
+          mbar_wait_spin(&tfull_bar[e], use & 1);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + e * p.col_stride;
           float m = MS_PAD_FILL;
