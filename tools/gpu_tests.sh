@@ -17,3 +17,6 @@ run dense "dense_tcgen05 or dense_duplicate or dense_rejects"
 echo "=== retrievers" | tee -a gpurun_out/tests.log
 timeout 900 python -m pytest tests/test_gpu_retrievers.py -m gpu -x -q > gpurun_out/test_retrievers.log 2>&1
 echo "exit $? : $(tail -1 gpurun_out/test_retrievers.log)" | tee -a gpurun_out/tests.log
+echo "=== fullsize" | tee -a gpurun_out/tests.log
+timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/test_fullsize.log 2>&1
+echo "exit $? : $(tail -1 gpurun_out/test_fullsize.log)" | tee -a gpurun_out/tests.log
