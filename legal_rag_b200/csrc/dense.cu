@@ -249,11 +249,14 @@ struct DenseSegments {
   int grid, g, slots, cap, first_cta, slot, k;
   template <class F> __device__ void operator()(F&& f) const {
     for (int i = threadIdx.x; i < k; i += SELECT_THREADS) { const uint64_t key = best[i]; if (key) f(key); }
-    for (int c = first_cta; c < grid; c += g) {
+    // one warp per CTA segment, several segments in flight: the loop is a chain of dependent global
+    // loads (count, then keys), so its latency is what a finalize costs at small query batches
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = first_cta + g * warp; c < grid; c += g * (SELECT_THREADS / 32)) {
       const size_t sidx = size_t(c) * slots + slot;
       const int n = cnt[sidx];
       const uint64_t* b = buf + sidx * cap;
-      for (int i = threadIdx.x; i < n; i += SELECT_THREADS) f(b[i]);
+      for (int i = lane; i < n; i += 32) f(b[i]);
     }
   }
 };
@@ -287,11 +290,11 @@ static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } re
 
 struct DensePlan {
   int grid, QB, g, slots, cap; int64_t DT;
-  size_t off_thr, off_cnt, off_best, off_buf, total;
+  size_t off_thr, off_cnt, off_best, off_buf, off_qpad, total;
   int64_t epoch0;    // tiles in the first epoch (a multiple of lcm(grid, QB)); later epochs grow 4x
 };
 
-static DensePlan dense_plan(int64_t N, int nq, int k, int sms) {
+static DensePlan dense_plan(int64_t N, int d, int nq, int k, int sms) {
   DensePlan pl;
   pl.QB = (nq + DENSE_BM - 1) / DENSE_BM;
   pl.DT = (N + DENSE_BN - 1) / DENSE_BN;
@@ -307,7 +310,10 @@ static DensePlan dense_plan(int64_t N, int nq, int k, int sms) {
   pl.off_best = pl.off_cnt + align_up(size_t(pl.grid) * pl.slots * 4, 256);
   pl.off_buf = pl.off_best + align_up(size_t(pl.QB) * DENSE_BM * k * 8, 256);
   pl.epoch0 = int64_t(pl.grid) / pl.g * pl.QB;
-  pl.total = pl.off_buf + size_t(pl.grid) * pl.slots * pl.cap * 8;
+  pl.off_qpad = pl.off_buf + align_up(size_t(pl.grid) * pl.slots * pl.cap * 8, 256);
+  // a query batch that does not fill its last 128-row block is copied into a zero-padded block: TMA boxes
+  // that hang over the end of the tensor are several times slower than in-bounds ones
+  pl.total = pl.off_qpad + (nq % DENSE_BM ? size_t(pl.QB) * DENSE_BM * size_t(d) * 2 : 0);
   return pl;
 }
 
@@ -316,9 +322,8 @@ static DensePlan dense_plan(int64_t N, int nq, int k, int sms) {
 using namespace lrag;
 
 extern "C" size_t lrag_dense_topk_workspace_bytes(int64_t N, int d, int nq, int k) {
-  (void)d;
-  if (N < 0 || nq <= 0 || k <= 0) return 0;
-  return dense_plan(N, nq, k, sm_count()).total;
+  if (N < 0 || nq <= 0 || k <= 0 || d <= 0) return 0;
+  return dense_plan(N, d, nq, k, sm_count()).total;
 }
 
 extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void* Q, int nq, int k,
@@ -332,7 +337,7 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
   LRAG_REQUIRE(Q && out_score && out_id && (X || N == 0), "dense_topk: null pointer");
   LRAG_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0,
                "dense_topk: X and Q must be 16-byte aligned");
-  const DensePlan pl = dense_plan(N, nq, k, sm_count());
+  const DensePlan pl = dense_plan(N, d, nq, k, sm_count());
   if (ws_bytes < pl.total || !ws) { set_error("dense_topk: workspace %zu < required %zu", ws_bytes, pl.total); return LRAG_ENOSPC; }
 
   DenseParams p;
@@ -354,7 +359,16 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
   const int P = next_pow2(k);
   if (N > 0) {
     CUtensorMap tq, tx;
-    int rc = make_tmap_bf16_2d(&tq, Q, uint64_t(nq), uint64_t(d), uint64_t(d), DENSE_BM, DENSE_BK);
+    const void* Qmap = Q;
+    uint64_t q_rows = uint64_t(nq);
+    if (nq % DENSE_BM) {
+      uint8_t* qpad = w + pl.off_qpad;
+      q_rows = uint64_t(pl.QB) * DENSE_BM;
+      LRAG_CHECK_CUDA(cudaMemsetAsync(qpad + size_t(nq) * d * 2, 0, (q_rows - nq) * size_t(d) * 2, stream));
+      LRAG_CHECK_CUDA(cudaMemcpyAsync(qpad, Q, size_t(nq) * d * 2, cudaMemcpyDeviceToDevice, stream));
+      Qmap = qpad;
+    }
+    int rc = make_tmap_bf16_2d(&tq, Qmap, q_rows, uint64_t(d), uint64_t(d), DENSE_BM, DENSE_BK);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tx, X, uint64_t(N), uint64_t(d), uint64_t(d), DENSE_BN, DENSE_BK);
     if (rc) return rc;
