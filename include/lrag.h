@@ -101,6 +101,13 @@ int lrag_topk_select_f32(const float* S, int64_t ld, int nq, int64_t N, int k, i
 int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
                     float* out_score, int64_t* out_id, lrag_stream_t stream);
 
+/* Gathered inner products: out_score[q, c] = <Q[q], X[rows[q, c]]> (rows outside [0, N) give -inf).
+ * Replaces the re-embedding + cosine loop of the graph-expansion channel
+ * (legalrag/retrieval/graph_retriever.py:177-186, `_cosine_sim` :20-22): neighbour chunks are index rows,
+ * their unit-norm embeddings are already in the corpus.  rows [nq, C] int64, local to the shard. */
+int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q, int nq,
+                                  const int64_t* rows, int C, float* out_score, lrag_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * BM25 channel.  Replaces `bm25.get_scores(tokens)` + the full Python sort at
  * legalrag/retrieval/bm25_retriever.py:74-75 (rank_bm25.BM25Okapi).

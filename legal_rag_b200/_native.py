@@ -34,6 +34,7 @@ SIGNATURES = {
     "lrag_dense_topk_bf16": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_dense_topk_ref_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
     "lrag_dense_topk_bf16_ref": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "lrag_dense_gather_scores_bf16": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_p, _c_int, _c_p, _c_p]),
     "lrag_topk_select_workspace_bytes": (_c_sz, [_c_int, _c_i64, _c_int]),
     "lrag_topk_select_f32": (_c_int, [_c_p, _c_i64, _c_int, _c_i64, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_topk_merge": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p]),

@@ -70,6 +70,21 @@ def dense_topk(X: torch.Tensor, Q: torch.Tensor, k: int, id_base: int = 0, *, re
     return s, i
 
 
+def gather_scores(X: torch.Tensor, Q: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    """Inner products of each query with a short list of corpus rows: X [N, d] bf16, Q [nq, d] bf16,
+    rows [nq, C] int64 (local rows; out-of-range = skipped) -> [nq, C] float32 (-inf for skipped)."""
+    lib = _native.init(X.device.index)
+    X = _need(X, torch.bfloat16, 2, "X")
+    Q = _need(Q, torch.bfloat16, 2, "Q")
+    rows = _need(rows, torch.int64, 2, "rows")
+    if Q.shape[1] != X.shape[1] or rows.shape[0] != Q.shape[0]:
+        raise LragError(f"gather_scores: shapes X{tuple(X.shape)} Q{tuple(Q.shape)} rows{tuple(rows.shape)} do not agree")
+    out = torch.empty(rows.shape, dtype=torch.float32, device=X.device)
+    check(lib.lrag_dense_gather_scores_bf16(_ptr(X), X.shape[0], X.shape[1], _ptr(Q), Q.shape[0], _ptr(rows), rows.shape[1],
+                                            _ptr(out), _stream()), "lrag_dense_gather_scores_bf16")
+    return out
+
+
 def dense_workspace_bytes(N: int, d: int, nq: int, k: int) -> int:
     return int(_native.load().lrag_dense_topk_workspace_bytes(N, d, nq, k))
 

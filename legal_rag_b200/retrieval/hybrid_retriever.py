@@ -85,7 +85,8 @@ class HybridRetriever:
                 print("[HybridRetriever] ColBERT init failed:", repr(e))
                 traceback.print_exc()
                 self.colbert = None
-        self.graph = None        # graph expansion is outside the accelerated path; plug a GraphRetriever in here
+        self.graph = None        # plug a retrieval.GraphRetriever(cfg, graph=<graph store with walk()>) in here: the graph
+                                 # store is host-side and injected, its scoring stage runs on the GPU
         self.reranker = None     # optional callable(question, hits) -> hits (cross-encoder rerank is out of scope)
 
     # ------------------------------------------------------------------ per-channel APIs

@@ -1,7 +1,7 @@
 """Generate tests/golden/* by EXECUTING the reference (only works where
 /root/reference exists; the outputs are committed so the GPU box never needs it).
 
-  python -m oracle.make_golden            # writes tests/golden/fuse_golden.json, ucc_corpus.npz
+  python -m oracle.make_golden            # writes tests/golden/fuse_golden.json, ucc_corpus.npz, graph_golden.json
 
 1. fuse_golden.json -- the reference's own ``HybridRetriever._fuse`` /
    ``_minmax`` / ``_rrf_with_breakdown`` / ``_dedup_keep_best``
@@ -175,6 +175,75 @@ def make_ucc_corpus() -> None:
     print("UCC: records", len(records), "docs", len(docs), "tokens", int(lens.sum()), "V", len(vocab))
 
 
+def make_graph_golden() -> None:
+    """graph_golden.json -- the scoring stage of the reference's GraphRetriever.search
+    (legalrag/retrieval/graph_retriever.py:85-219) run unmodified on fake collaborators: a graph whose
+    walk() returns a fixed node list, and a store whose _embed() returns fixed vectors per text."""
+    _stub_modules()
+    sys.path.insert(0, str(REF))
+    from legalrag.config import RetrievalConfig
+    from legalrag.retrieval import graph_retriever as gr
+    from legalrag.schemas import LawChunk
+
+    rng = np.random.default_rng(31)
+    d, n = 64, 40
+    vecs = rng.standard_normal((n, d)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    qvec = rng.standard_normal(d).astype(np.float32)
+    qvec /= np.linalg.norm(qvec)
+    chunks = [LawChunk(id=f"c{i}", law_name="L", article_no=str(i), article_id=f"a{i}", text=f"text {i}",
+                       lang="en" if i % 5 else "zh") for i in range(n)]
+    chunks[7].text = "   "                                        # blank text: dropped (:150)
+    text2vec = {c.text: vecs[i] for i, c in enumerate(chunks)}
+    rel_pool = [[], ["cite"], ["next"], ["defined_by", "next"], ["neighbor"], ["amend"], ["CITED"], ["unknown_rel"], ["prev", "ref"]]
+
+    class Node(SimpleNamespace):
+        pass
+
+    nodes = []
+    for j in range(60):
+        i = int(rng.integers(0, n + 3))                           # a few article ids are not in the store (:148-150)
+        nodes.append(Node(article_id=f"a{i}", graph_depth=int(rng.integers(0, 4)), relations=rel_pool[j % len(rel_pool)],
+                          meta={"_edge_conf": float(rng.choice([1.0, 0.9, 0.5, 0.0]))} if j % 3 else {}))
+    nodes.append(Node(article_id="", graph_depth=1, relations=[], meta={}))
+
+    class Store:
+        def _embed(self, texts, is_query=False):
+            if isinstance(texts, str):
+                return qvec
+            return np.stack([text2vec[t] for t in texts])
+
+    class Graph:
+        def walk(self, **kw):
+            self.kw = kw
+            return nodes
+
+    cases = []
+    for lang, top_k, gamma in ((None, 10, 0.7), ("en", 50, 0.7), (None, 5, 1.3)):
+        ret = object.__new__(gr.GraphRetriever)
+        base = RetrievalConfig()          # has no graph_depth_gamma field: the reference's getattr default (0.7) applies
+        rcfg = SimpleNamespace(graph_walk_depths=base.graph_walk_depths, graph_limit=base.graph_limit,
+                               graph_rel_types=base.graph_rel_types, graph_min_conf=0.0, graph_depth_gamma=gamma)
+        ret.cfg = SimpleNamespace(retrieval=rcfg)
+        ret.graph, ret.store = Graph(), Store()
+        ret.id2chunk = {c.article_id: c for c in chunks}
+        seeds = [SimpleNamespace(chunk=chunks[0]), SimpleNamespace(chunk=chunks[3])]
+        hits = ret.search("the question", seeds, lang=lang, top_k=top_k)
+        cases.append({"lang": lang, "top_k": top_k, "gamma": gamma,
+                      "hits": [{"id": h.chunk.id, "score": h.score, "rank": h.rank, "source": h.source,
+                                "breakdown": {k: h.score_breakdown[k] for k in ("semantic", "depth_decay", "relation_weight", "edge_conf", "final", "graph_depth")}}
+                               for h in hits]})
+    out = {"d": d, "vectors": vecs.tolist(), "qvec": qvec.tolist(),
+           "chunks": [c.model_dump() for c in chunks],
+           "nodes": [{"article_id": x.article_id, "graph_depth": x.graph_depth, "relations": x.relations, "meta": x.meta} for x in nodes],
+           "cases": cases,
+           "functions": {"depth_decay": [[dpt, g, gr._depth_decay(dpt, gamma=g)] for dpt in (-1, 0, 1, 2, 5) for g in (0.7, 1.0)],
+                         "relation_weight": [[r, gr._relation_weight(r)] for r in rel_pool]}}
+    (OUT / "graph_golden.json").write_text(json.dumps(out))
+    print("graph golden:", [len(c["hits"]) for c in cases])
+
+
 if __name__ == "__main__":
     make_ucc_corpus()
     make_fuse_golden()
+    make_graph_golden()

@@ -420,3 +420,19 @@ def test_hybrid_shard_matches_oracle_pipeline(eng):
             m = min(len(ref), k + 8)
             check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
                               k, 2e-3, what=f"hybrid-{method}")
+
+
+# ---------------------------------------------------------------- gathered inner products (graph-expansion scoring)
+@pytest.mark.parametrize("N,d,nq,C", [(500, 768, 1, 800), (64, 64, 3, 10), (3000, 1024, 17, 33), (10, 8, 2, 5)])
+def test_gather_scores_match_numpy(eng, N, d, nq, C):
+    rng = np.random.default_rng(N + C)
+    Xd, Xr = _bf16(_unit(rng, (N, d)))
+    Qd, Qr = _bf16(_unit(rng, (nq, d)))
+    rows = rng.integers(0, N, (nq, C)).astype(np.int64)
+    rows[0, 0] = -1
+    rows[-1, -1] = N              # out of range -> -inf
+    got = eng.gather_scores(Xd, Qd, torch.from_numpy(rows).cuda()).cpu().numpy()
+    want = np.einsum("qd,qcd->qc", Qr, Xr[np.clip(rows, 0, N - 1)])
+    ok = (rows >= 0) & (rows < N)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=1e-4, atol=1e-5)
+    assert np.isneginf(got[~ok]).all()

@@ -161,3 +161,49 @@ def test_incremental_add_is_searchable_and_persisted(world):
     # ids that are already indexed are skipped (incremental_dense_builder.py:51-58)
     assert builders.IncrementalDenseBuilder(cfg, store).add_chunks([new, new]) == 0
     assert store.index.ntotal == n0 + 1
+
+
+def test_graph_retriever_scoring_matches_reference_golden(golden_dir, tmp_path):
+    """retrieval.GraphRetriever (gathered inner products on the GPU) against the hits the reference's own
+    GraphRetriever.search produced for the same nodes and vectors (tests/golden/graph_golden.json)."""
+    import json
+    from types import SimpleNamespace
+    from legal_rag_b200.retrieval import GraphRetriever, GpuFlatIndex
+    from legal_rag_b200.schemas import LawChunk
+    g = json.load(open(os.path.join(golden_dir, "graph_golden.json")))
+    vecs, qvec = np.array(g["vectors"], dtype=np.float32), np.array(g["qvec"], dtype=np.float32)
+    chunks = [LawChunk(**c) for c in g["chunks"]]
+    nodes = [SimpleNamespace(**n) for n in g["nodes"]]
+
+    class Store:                                  # the slice of VectorStore the channel uses
+        def __init__(self):
+            self.index, self.chunks = GpuFlatIndex.from_numpy(vecs), chunks
+        def load(self):
+            pass
+        def _embed(self, texts, is_query=False):
+            return qvec[None, :]
+
+    class Graph:
+        def walk(self, **kw):
+            return nodes
+
+    for case in g["cases"]:
+        rcfg = SimpleNamespace(graph_walk_depths={"default": 2}, graph_limit=800, graph_rel_types=None, graph_min_conf=0.0,
+                               graph_depth_gamma=case["gamma"])
+        gr = GraphRetriever(SimpleNamespace(retrieval=rcfg), graph=Graph(), store=Store())
+        hits = gr.search("the question", [SimpleNamespace(chunk=chunks[0])], lang=case["lang"], top_k=case["top_k"])
+        want = case["hits"]
+        row = {c.id: i for i, c in enumerate(chunks)}
+        # the golden list is already cut at top_k, so the last tie run may only be matched as a subset
+        check_topk_parity(np.array([[h.score for h in hits]]), np.array([[row[h.chunk.id] for h in hits]]),
+                          np.array([[h["score"] for h in want]]), np.array([[row[h["id"]] for h in want]]), len(want), 1e-2,
+                          what="graph", floor=0.1)
+        assert all(h.source == "graph" and h.rank == r for r, h in enumerate(hits, start=1))
+        by_id = {h["id"]: h for h in want}
+        for h in hits:
+            if h.chunk.id in by_id:
+                b = by_id[h.chunk.id]["breakdown"]
+                assert h.score_breakdown["depth_decay"] == pytest.approx(b["depth_decay"], rel=1e-9)
+                assert h.score_breakdown["relation_weight"] == b["relation_weight"] and h.score_breakdown["edge_conf"] == b["edge_conf"]
+                assert h.score_breakdown["graph_depth"] == b["graph_depth"]
+                assert h.score_breakdown["semantic"] == pytest.approx(b["semantic"], abs=5e-3)     # bf16 corpus rows

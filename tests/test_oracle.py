@@ -149,3 +149,24 @@ def test_maxsim_oracle_masking_and_skip():
     assert S[0, 1] == pytest.approx(ref, rel=1e-6)
     s, i = omaxsim.rerank_topk(Q, D, doclen, cand, 4)
     assert i[0, 3] == -1 and set(i[0, :3].tolist()) == {0, 1, 3}
+
+
+def test_graph_scoring_restatement_matches_reference_execution(golden_dir):
+    """oracle/graph.py against tests/golden/graph_golden.json (the reference's GraphRetriever.search executed)."""
+    from oracle import graph as ograph
+    g = json.load(open(os.path.join(golden_dir, "graph_golden.json")))
+    for dpt, gamma, want in g["functions"]["depth_decay"]:
+        assert ograph.depth_decay(dpt, gamma) == pytest.approx(want, rel=1e-12)
+    for rels, want in g["functions"]["relation_weight"]:
+        assert ograph.relation_weight(rels) == want
+    vecs, q = np.array(g["vectors"], dtype=np.float32), np.array(g["qvec"], dtype=np.float32)
+    chunks = g["chunks"]
+    id2row = {c["article_id"]: i for i, c in enumerate(chunks)}
+    for case in g["cases"]:
+        got = ograph.graph_hits(q, g["nodes"], id2row, vecs, [c["text"] for c in chunks], [c.get("lang") for c in chunks],
+                                lang=case["lang"], top_k=case["top_k"], gamma=case["gamma"])
+        assert [chunks[h["row"]]["id"] for h in got] == [h["id"] for h in case["hits"]]
+        for a, b in zip(got, case["hits"]):
+            assert a["score"] == pytest.approx(b["score"], rel=1e-6, abs=1e-9) and a["rank"] == b["rank"]
+            for key in ("semantic", "depth_decay", "relation_weight", "edge_conf", "graph_depth"):
+                assert a[key] == pytest.approx(b["breakdown"][key], rel=1e-6, abs=1e-9)
