@@ -62,7 +62,8 @@ constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
 constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
-constexpr int BM25_GATHER_MAX = 32;                  // runs this short share one ring stage (one lane per posting)
+constexpr int BM25_GATHER_MAX = 64;                  // runs this short share one ring stage (32 runs x 64 postings fill it at most)
+static_assert(32 * BM25_GATHER_MAX <= BM25_CHUNK, "a gather stage must hold one lane batch of short runs");
 enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
 
 struct Bm25Ws {
@@ -434,7 +435,7 @@ bm25_scan_kernel(const Bm25Params p) {
       __syncwarp();
     };
     // Short runs (rare terms: a handful of postings per slab) with the same multiplier share ONE
-    // stage: lane l copies posting l of each run with 4-byte asynchronous copies packed back to back,
+    // stage: the lanes copy each run with 4-byte asynchronous copies packed back to back,
     // and the stage's barrier completes when every lane's copies have landed.
     auto emit_gather = [&](uint32_t runs, int64_t first, int cnt, float mult, int sl0, int flags) {
       const int s = stage_acquire();
@@ -447,9 +448,9 @@ bm25_scan_kernel(const Bm25Params p) {
         runs &= runs - 1;
         const int64_t f = __shfl_sync(0xffffffffu, first, src);
         const int c = __shfl_sync(0xffffffffu, cnt, src);
-        if (lane < c) {
-          cp_async_4(dst_id + total + lane, p.doc_id + f + lane);
-          cp_async_4(dst_imp + total + lane, p.impact + f + lane);
+        for (int l = lane; l < c; l += 32) {
+          cp_async_4(dst_id + total + l, p.doc_id + f + l);
+          cp_async_4(dst_imp + total + l, p.impact + f + l);
         }
         total += c;
       }
