@@ -2,10 +2,11 @@
 // `bm25.get_scores(tokens)` and the full Python sort at legalrag/retrieval/bm25_retriever.py:74-75
 // of the reference; rank_bm25.BM25Okapi semantics, see oracle/bm25.py).
 //
-// HBM/L2-bound integer/float streaming work, no tensor cores.
+// Integer/float streaming work over posting lists, no tensor cores; HBM sees every posting range once,
+// the rest is served from L2, so the binding resource is the SM side (issue slots, shared memory).
 //
 // Work decomposition.  A *chain* is one (query, doc split) pair; it walks its split in *items* of
-// `item_slabs` slabs (BM25_SLAB docs = 64 KB of fp32 accumulators in shared memory).  Items are
+// `item_slabs` slabs (BM25_SLAB docs = 48 KB of int32 fixed-point accumulators in shared memory).  Items are
 // numbered step-major -- item = step * n_chains + chain -- and handed out by an atomic counter to
 // persistent CTAs, so at any moment the whole machine works on the same narrow doc range of every
 // query: a posting list is fetched from HBM once per range and then served from L2 to all the other
@@ -18,12 +19,14 @@
 //   * bounds warp   -- claims the next item, loads the chain's term cursors and finds the posting
 //                      boundaries of every query term at every slab edge with one parallel round of
 //                      windowed binary searches (postings are doc-id sorted); double-buffered, one
-//                      group of slabs ahead of the copy warp;
-//   * copy warp     -- walks the (slab, term) runs in order and streams them, <= BM25_CHUNK postings at
-//                      a time, into a shared-memory ring with bulk async copies (cp.async.bulk, 16-byte
-//                      aligned source windows) that complete on mbarriers.  Each ring stage carries a
-//                      descriptor {count, skip, term multiplicity, slab base, flags}: the consumers
-//                      are a plain interpreter of that stream;
+//                      group of slabs ahead of the copy warps;
+//   * 3 copy warps  -- walk the (slab, term) runs in order (the lanes look up one term each) and stream
+//                      them, <= BM25_CHUNK postings at a time, into a shared-memory ring with bulk async
+//                      copies (cp.async.bulk, 16-byte aligned source windows) that complete on mbarriers;
+//                      chunk c is issued by warp c mod 3.  The short runs of a slab (rare terms) are
+//                      packed into ONE stage with 4-byte cp.async copies.  Each ring stage carries a
+//                      descriptor {count, skip, term multiplicity x scale, slab base, flags}: the
+//                      consumers are a plain interpreter of that stream;
 //   * 16 consumer warps -- per stage add `mult * impact` into acc[doc - slab0] with one shared-memory
 //                      integer atomic per posting: scores are kept in fixed point (int32, a per-query
 //                      power-of-two scale sized from `impact_bound`), so adds commute exactly, the
@@ -55,7 +58,7 @@ constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
 constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
 constexpr int BM25_CHUNK = 2048;                     // postings per ring stage
-constexpr int BM25_STAGES = 3;                       // 64 KB slab + 24 KB ring + 8 KB candidates + state: two CTAs per SM
+constexpr int BM25_STAGES = 3;                       // 48 KB slab + 48 KB ring + 4 KB candidates + 11 KB state: two CTAs per SM
 constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
