@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|bm25|hybrid]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|maxsim_scan|bm25|hybrid]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
@@ -448,7 +448,73 @@ class HybridWorkload:
     cpu_cores = 1
 
 
-WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "bm25": Bm25Workload, "hybrid": HybridWorkload}
+class MaxsimScanWorkload:
+    """SURVEY 8d C3, tensor-bound variant: exact full-corpus MaxSim of a query batch against configs[2]'s token store
+    (1M docs x 128 tokens x 128-d) -- what the reference's ColBERT channel approximates with PLAID."""
+    name = "maxsim_full_scan"
+    dtype = "bf16"
+    dominant = "maxsim_scan"
+
+    def __init__(self, args, rank, world, device):
+        self.Nd, self.Ld, self.Lq = args.n_docs or 1_000_000, 128, 32
+        self.nq, self.k = args.nq or 64, args.k
+        self.rank, self.world, self.device = rank, world, device
+
+    def config(self):
+        return {"workload": f"configs[2] token store, full scan: {self.Nd} docs x {self.Ld} x 128 bf16, batch of {self.nq} queries x {self.Lq} tokens "
+                            f"against every document -> top-{self.k}", "l2": f"token store {self.Nd * self.Ld * 256 / 1e9:.1f} GB >> L2",
+                "parallelism": f"doc-sharded x{self.world}" if self.world > 1 else "single GPU"}
+
+    def setup(self):
+        import torch
+        from legal_rag_b200 import engine, synth
+        self.torch, self.engine = torch, engine
+        self.D = synth.unit_tokens_bf16(self.Nd, self.Ld, 128, 5 + self.rank, self.device)
+        self.Q = synth.unit_tokens_bf16(self.nq, self.Lq, 128, 7, self.device)
+        self.Q_host = self.Q.cpu().pin_memory()
+
+    def step(self):
+        s, i = self.engine.maxsim_scan_topk(self.D, None, self.Q, self.k, id_base=self.rank * self.Nd)
+        return self.engine.allgather_merge(s, i, self.k)
+
+    def e2e_step(self):
+        q = self.Q_host.to(self.device, non_blocking=True)
+        s, i = self.engine.maxsim_scan_topk(self.D, None, q, self.k, id_base=self.rank * self.Nd)
+        s, i = self.engine.allgather_merge(s, i, self.k)
+        return s.cpu(), i.cpu()
+
+    def e2e_bytes(self):
+        return self.nq * self.Lq * 128 * 2, self.nq * self.k * 12
+
+    def units_per_step(self):
+        return self.nq * self.world
+
+    def roofline(self, kernel_ms, peaks):
+        flops = 2.0 * self.nq * self.Lq * 128 * self.Nd * self.Ld
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "traffic": None, "kernel": "maxsim_scan_kernel", "kernel_ms": kernel_ms,
+                "algorithmic": f"2*nq*Lq*dim*Nd*Ld = {flops:.3e} FLOP per step", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
+                "scan_gbs": self.Nd * self.Ld * 256 / (kernel_ms * 1e-3) / 1e9}
+
+    def cpu_sample(self, budget_s=15.0):
+        import numpy as np
+        from oracle import maxsim as omaxsim
+        n_s, nq_s = 2000, 4
+        rng = np.random.default_rng(5)
+        D = rng.standard_normal((n_s, self.Ld, 128), dtype=np.float32)
+        Q = rng.standard_normal((nq_s, self.Lq, 128), dtype=np.float32)
+        cand = np.tile(np.arange(n_s), (nq_s, 1))
+
+        def run():
+            t0 = time.perf_counter()
+            omaxsim.rerank_topk(Q, D, None, cand, self.k)
+            dt = time.perf_counter() - t0
+            return nq_s / (dt * self.Nd / n_s), dt
+        return run, f"oracle numpy-fp32 MaxSim of {nq_s} queries against {n_s} documents per step, extrapolated linearly in documents to {self.Nd}"
+
+
+WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "maxsim_scan": MaxsimScanWorkload, "bm25": Bm25Workload, "hybrid": HybridWorkload}
 
 
 # =================================================================================================

@@ -157,6 +157,20 @@ int lrag_maxsim_scores_bf16(const void* D, const int32_t* doclen, int64_t Nd, in
                             const void* Q, int nq, int Lq, const int64_t* cand, int C,
                             float* out_score, lrag_stream_t stream);
 
+/* Full-corpus MaxSim for a query batch (the reference's ColBERT channel is a first-stage retriever over
+ * the whole corpus, colbert_retriever.py:152; PLAID approximates this scan): one tensor-core contraction
+ * of all query-token rows against all doc-token rows with a MaxSim epilogue out of TMEM, the token store
+ * is read from HBM once per batch.  Ld must be 32, 64, 128 or 256.  `scores` writes the [nq, Nd] matrix
+ * (row stride ld_out >= Nd, -9999 * Lq for empty documents); `topk` ranks it (ids = id_base + row).
+ * Workspace: lrag_maxsim_scan_workspace_bytes(Nd, nq, k) with k = 0 for the scores entry point. */
+size_t lrag_maxsim_scan_workspace_bytes(int64_t Nd, int nq, int k);
+int lrag_maxsim_scan_scores_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim,
+                                 const void* Q, int nq, int Lq, float* out_score, int64_t ld_out,
+                                 void* ws, size_t ws_bytes, lrag_stream_t stream);
+int lrag_maxsim_scan_topk_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim,
+                               const void* Q, int nq, int Lq, int k, int64_t id_base, float* out_score,
+                               int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
+
 /* ---------------------------------------------------------------------------------
  * Fusion.  Replaces HybridRetriever._fuse (legalrag/retrieval/hybrid_retriever.py:389-551,
  * _minmax :24-30, _rrf_with_breakdown :33-56) plus the min_final_score filter (:309-310)

@@ -46,6 +46,10 @@ SIGNATURES = {
     "lrag_maxsim_rerank_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_p, _c_int, _c_int,
                                          _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_maxsim_scores_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_p, _c_int, _c_p, _c_p]),
+    "lrag_maxsim_scan_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int]),
+    "lrag_maxsim_scan_scores_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_p, _c_i64, _c_p, _c_sz, _c_p]),
+    "lrag_maxsim_scan_topk_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_p, _c_p,
+                                            _c_p, _c_sz, _c_p]),
     "lrag_fuse_topk": (_c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_int, _c_int, _c_int, _c_f64, _c_f64, _c_f64,
                                 _c_int, _c_f64, _c_f64, _c_p, _c_p, _c_p, _c_p]),
 }

@@ -28,7 +28,7 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
                       uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 
 // optional per-launch timing of the dominant kernels (lrag_prof_enable / lrag_prof_collect)
-enum ProfTag { PROF_DENSE_SCAN = 0, PROF_BM25_SCAN = 1, PROF_MAXSIM = 2, PROF_FUSE = 3, PROF_SELECT = 4 };
+enum ProfTag { PROF_DENSE_SCAN = 0, PROF_BM25_SCAN = 1, PROF_MAXSIM = 2, PROF_FUSE = 3, PROF_SELECT = 4, PROF_MAXSIM_SCAN = 5 };
 void prof_begin(cudaStream_t stream, int tag);
 void prof_end(cudaStream_t stream);
 void note_launch(int n = 1);   // every kernel the library launches is counted (lrag_launch_count)

@@ -1,0 +1,299 @@
+// ColBERT channel, full-corpus mode for query batches: MaxSim of EVERY document against a batch of queries
+// (the reference's ColBERT channel is a first-stage retriever over the whole corpus,
+// legalrag/retrieval/colbert_retriever.py:152 / hybrid_retriever.py:299; PLAID approximates this scan).
+//
+// maxsim_kernel (maxsim.cu) gathers candidates per query: every query re-reads the token rows it scores,
+// which is the right shape for a rerank (HBM-bound, 32 FLOP/B).  A batch that scans the whole store would
+// re-read it once per query; this kernel instead runs ONE tensor-core contraction
+//     [nq x 32 query-token rows, 128] . [Nd x Ld doc-token rows, 128]^T
+// (persistent CTAs, the CTA's 4-query block resident in shared memory as the A operand, doc tiles streamed
+// by TMA through a 3-stage ring, tcgen05 128 x 256 tiles, accumulators double-buffered in TMEM; the CTAs that
+// hold different query blocks walk the doc tiles in step, so the store is read from HBM once) and a MaxSim epilogue: a tile row block of 32 TMEM lanes is one query's tokens,
+// a run of Ld columns is one document; each lane takes the max over the document's (unmasked) columns,
+// one shuffle tree sums over the query's tokens, lane 0 writes score[query, doc].  The [Lq, Ld]
+// similarity matrices never leave TMEM; what is written is the [nq, Nd] per-document score matrix
+// (1/4096 of the token-level products), ranked by lrag_topk_select_f32.
+// Arithmetic intensity = nq * 32 / ... >= 2048 FLOP per store byte at 64 queries: tensor-bound.
+#include "common.cuh"
+#include "select.cuh"
+
+namespace lrag {
+
+constexpr int SC_BM = 128;            // 4 queries x 32 token rows (UMMA M)
+constexpr int SC_BN = 256;            // doc-token rows per tile   (UMMA N)
+constexpr int SC_BK = 64;             // one 128 B swizzle row of bf16
+constexpr int SC_DIM = 128;
+constexpr int SC_KB = SC_DIM / SC_BK;
+constexpr int SC_STAGES = 3;          // doc tiles in flight (a stage = one whole 256 x 128 doc tile, 64 KB)
+constexpr int SC_A_BYTES = SC_BM * SC_DIM * 2;        // 32 KB: the CTA's query block, resident for a whole pass
+constexpr int SC_B_BYTES = SC_BN * SC_DIM * 2;        // 64 KB
+constexpr int SC_EPI_WARPS = 8;       // two per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int SC_PART_BYTES = 2 * 4 * 32 * 4;         // partial maxima exchanged when Ld = 256
+constexpr int SC_SMEM = SC_A_BYTES + SC_STAGES * SC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + SC_PART_BYTES;
+constexpr float SC_PAD_FILL = -9999.0f;   // value of a masked (padding) doc token, as in maxsim.cu / the oracle
+
+struct ScanParams {
+  const int32_t* doclen;
+  float* out;          // [nq, ld_out]
+  int64_t Nd, ld_out;
+  int Ld, Lq, nq, QB;
+  int64_t DT;          // doc tiles
+  int P, L;            // P query blocks are in flight at a time, L CTAs share each of them
+};
+
+// Work split: CTA c serves query block (pass * P + c % P) in pass `pass` and takes the doc tiles
+// c / P, c / P + L, ... of it.  The query block stays in shared memory for the whole pass (it is the A operand
+// of every tile), only doc tiles stream; the P CTAs that hold different query blocks walk the doc tiles in step,
+// so a doc tile comes from HBM once and from L2 for the others.
+__global__ void __launch_bounds__(SC_THREADS, 1)
+maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, const ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SC_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SC_STAGES * SC_B_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES] doc tile landed
+  uint64_t* empty_bar = bars + SC_STAGES;          // [STAGES] doc tile consumed by the MMAs
+  uint64_t* tfull_bar = bars + 2 * SC_STAGES;      // [2] accumulator ready
+  uint64_t* tempty_bar = bars + 2 * SC_STAGES + 2; // [2] accumulator drained
+  uint64_t* afull_bar = bars + 2 * SC_STAGES + 4;  // query block landed
+  uint64_t* aempty_bar = bars + 2 * SC_STAGES + 5; // last MMA of the pass retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SC_STAGES + 6);
+  float* part = reinterpret_cast<float*>(smem_b + SC_STAGES * SC_B_BYTES + 256);   // [2 buffers][4 quads][32 lanes]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int my_slot = blockIdx.x % p.P, my_lane = blockIdx.x / p.P;
+  const bool active = my_lane < p.L;
+  const int passes = (p.QB + p.P - 1) / p.P;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_d);
+    for (int s = 0; s < SC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], SC_EPI_WARPS); }
+    mbar_init(afull_bar, 1); mbar_init(aempty_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0 && active) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pass = 0; pass < passes; ++pass) {
+        const int qb = pass * p.P + my_slot;
+        if (qb >= p.QB) break;
+        mbar_wait(aempty_bar, (pass & 1) ^ 1);
+        mbar_arrive_expect_tx(afull_bar, SC_A_BYTES);
+        for (int kb = 0; kb < SC_KB; ++kb)
+          tma_load_2d(smem_a + kb * (SC_BM * SC_BK * 2), &tmap_q, afull_bar, kb * SC_BK, qb * SC_BM);
+        for (int64_t dt = my_lane; dt < p.DT; dt += p.L) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sb = smem_b + stage * SC_B_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
+          for (int kb = 0; kb < SC_KB; ++kb)
+            tma_load_2d(sb + kb * (SC_BN * SC_BK * 2), &tmap_d, &full_bar[stage], kb * SC_BK, int32_t(dt * SC_BN));
+          if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0 && active) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_BN);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int pass = 0; pass < passes; ++pass) {
+        if (pass * p.P + my_slot >= p.QB) break;
+        mbar_wait(afull_bar, pass & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a);
+        for (int64_t dt = my_lane; dt < p.DT; dt += p.L, ++it) {
+          const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + as * SC_BN;
+          const uint32_t b_addr = smem_u32(smem_b + stage * SC_B_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < SC_KB; ++kb) {
+            const uint64_t da = umma_desc_k_sw128(a_addr + kb * (SC_BM * SC_BK * 2));
+            const uint64_t db = umma_desc_k_sw128(b_addr + kb * (SC_BN * SC_BK * 2));
+#pragma unroll
+            for (int kk = 0; kk < SC_BK / 16; ++kk)
+              umma_bf16_ss(tmem_d, da + uint64_t(kk * 2), db + uint64_t(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tfull_bar[as]);
+          if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(aempty_bar);                   // the query block may be replaced once these MMAs retire
+      }
+    }
+  } else if (active) {
+    // ===================== epilogue: max over a document's tokens, sum over the query's tokens =====
+    // Two warps per TMEM lane quadrant (= query inside the block); each takes one half of the tile's
+    // columns.  With Ld = 256 the single document spans both halves: the partial maxima meet in smem.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int dpt = SC_BN / p.Ld;                  // documents per tile
+    uint32_t it = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int qb = pass * p.P + my_slot;
+      if (qb >= p.QB) break;
+      const int q = qb * 4 + quad;
+      for (int64_t dt = my_lane; dt < p.DT; dt += p.L, ++it) {
+        const int64_t doc0 = dt * dpt;
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        // document lengths of the tile, fetched before the accumulator is waited for
+        int dl_mine = 0;
+        if (lane < dpt) {
+          const int64_t doc = doc0 + lane;
+          dl_mine = doc < p.Nd ? (p.doclen ? min(p.doclen[doc], p.Ld) : p.Ld) : 0;
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
+        float m = SC_PAD_FILL;
+#pragma unroll 1
+        for (int c = half * (SC_BN / 64); c < (half + 1) * (SC_BN / 64); ++c) {
+          const int col = c * 32;
+          const int din = col / p.Ld, off = col - din * p.Ld;
+          const int dl = __shfl_sync(0xffffffffu, dl_mine, din);
+          if (off < dl) {                            // warp-uniform: the chunk holds unmasked tokens
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + col, v);
+            tmem_ld_wait();
+            if (off + 32 <= dl) {
+              float m4[4];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float x = __uint_as_float(v[g * 8]);
+#pragma unroll
+                for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(v[g * 8 + j]));
+                m4[g] = x;
+              }
+              m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (off + j < dl) m = fmaxf(m, __uint_as_float(v[j]));
+            }
+          }
+          const bool doc_ends = off + 32 == p.Ld;
+          const bool half_ends = p.Ld == SC_BN && c == SC_BN / 64 - 1;     // first half of a 256-token document
+          if (half_ends) {
+            part[(as * 4 + quad) * 32 + lane] = m;   // handed to the warp that owns the second half
+          } else if (doc_ends) {
+            if (p.Ld == SC_BN) {
+              asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");     // partner's partial maximum is in smem
+              m = fmaxf(m, part[(as * 4 + quad) * 32 + lane]);
+            }
+            float sum = (lane < p.Lq) ? m : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const int64_t doc = doc0 + din;
+            if (lane == 0 && q < p.nq && doc < p.Nd) p.out[size_t(q) * p.ld_out + doc] = sum;
+            m = SC_PAD_FILL;
+          }
+        }
+        if (p.Ld == SC_BN && half == 0) asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base, const int64_t* col_id,
+                       float* out_score, int64_t* out_id, cudaStream_t stream);
+
+static size_t scan_qpad_bytes(int nq) { return align_up(size_t((nq + 3) / 4) * SC_BM * SC_DIM * 2, 256); }
+
+static int scan_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim, const void* Q, int nq, int Lq,
+                       float* out, int64_t ld_out, void* qpad, cudaStream_t stream) {
+  LRAG_REQUIRE(initialised(), "lrag_init has not been called");
+  LRAG_REQUIRE(dim == SC_DIM, "maxsim_scan: dim=%d, only 128-d token vectors are supported", dim);
+  LRAG_REQUIRE(Ld >= 32 && Ld <= 256 && SC_BN % Ld == 0, "maxsim_scan: Ld=%d must be 32, 64, 128 or 256 (documents tile the 256-row block)", Ld);
+  LRAG_REQUIRE(Lq >= 1 && Lq <= 32, "maxsim_scan: Lq=%d must be in [1, 32]", Lq);
+  LRAG_REQUIRE(nq > 0 && Nd > 0 && ld_out >= Nd, "maxsim_scan: empty problem or short output rows (nq=%d Nd=%lld ld=%lld)", nq, (long long)Nd, (long long)ld_out);
+  LRAG_REQUIRE(Nd * int64_t(Ld) < (int64_t(1) << 31), "maxsim_scan: token store of %lld x %d rows exceeds one shard", (long long)Nd, Ld);
+  LRAG_REQUIRE(D && Q && out && qpad, "maxsim_scan: null pointer");
+  LRAG_REQUIRE((reinterpret_cast<uintptr_t>(D) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0,
+               "maxsim_scan: D and Q must be 16-byte aligned");
+  ScanParams p;
+  p.doclen = doclen; p.out = out; p.Nd = Nd; p.ld_out = ld_out; p.Ld = Ld; p.Lq = Lq; p.nq = nq;
+  p.QB = (nq + 3) / 4;
+  p.DT = (Nd * Ld + SC_BN - 1) / SC_BN;
+  // queries as 32-row blocks: [nq, Lq, 128] -> zero-padded [QB * 4, 32, 128] (in-bounds TMA boxes, zero rows add 0)
+  LRAG_CHECK_CUDA(cudaMemsetAsync(qpad, 0, scan_qpad_bytes(nq), stream));
+  LRAG_CHECK_CUDA(cudaMemcpy2DAsync(qpad, 32 * SC_DIM * 2, Q, size_t(Lq) * SC_DIM * 2, size_t(Lq) * SC_DIM * 2, nq,
+                                    cudaMemcpyDeviceToDevice, stream));
+  CUtensorMap tq, td;
+  int rc = make_tmap_bf16_2d(&tq, qpad, uint64_t(p.QB) * SC_BM, SC_DIM, SC_DIM, SC_BM, SC_BK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&td, D, uint64_t(Nd) * Ld, SC_DIM, SC_DIM, SC_BN, SC_BK);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LRAG_CHECK_CUDA(cudaFuncSetAttribute(maxsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  p.P = p.QB < sms ? p.QB : sms;                                       // query blocks in flight
+  int64_t L = sms / p.P;                                               // CTAs per query block
+  if (L > p.DT) L = p.DT;
+  p.L = int(L < 1 ? 1 : L);
+  const int grid = p.P * p.L;
+  prof_begin(stream, PROF_MAXSIM_SCAN);
+  maxsim_scan_kernel<<<grid, SC_THREADS, SC_SMEM, stream>>>(tq, td, p);
+  prof_end(stream);
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+  return LRAG_OK;
+}
+
+}  // namespace lrag
+
+using namespace lrag;
+
+extern "C" size_t lrag_maxsim_scan_workspace_bytes(int64_t Nd, int nq, int k) {
+  if (Nd <= 0 || nq <= 0) return 0;
+  // padded query block (+ the [nq, Nd] score matrix when the top-k entry point is used: k > 0)
+  return scan_qpad_bytes(nq) + (k > 0 ? align_up(size_t(nq) * size_t(Nd) * 4, 256) : 0);
+}
+
+extern "C" int lrag_maxsim_scan_scores_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim, const void* Q,
+                                            int nq, int Lq, float* out_score, int64_t ld_out, void* ws, size_t ws_bytes,
+                                            lrag_stream_t stream) {
+  const size_t need = lrag_maxsim_scan_workspace_bytes(Nd, nq, 0);
+  if (ws_bytes < need || !ws) { set_error("maxsim_scan_scores: workspace %zu < required %zu", ws_bytes, need); return LRAG_ENOSPC; }
+  return scan_launch(D, doclen, Nd, Ld, dim, Q, nq, Lq, out_score, ld_out, ws, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lrag_maxsim_scan_topk_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim, const void* Q,
+                                          int nq, int Lq, int k, int64_t id_base, float* out_score, int64_t* out_id,
+                                          void* ws, size_t ws_bytes, lrag_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LRAG_REQUIRE(k > 0 && k <= LRAG_MAX_K, "maxsim_scan_topk: need 1 <= k <= %d (k=%d)", LRAG_MAX_K, k);
+  LRAG_REQUIRE(out_score && out_id, "maxsim_scan_topk: null output");
+  const size_t need = lrag_maxsim_scan_workspace_bytes(Nd, nq, k);
+  if (ws_bytes < need || !ws) { set_error("maxsim_scan_topk: workspace %zu < required %zu", ws_bytes, need); return LRAG_ENOSPC; }
+  float* S = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + scan_qpad_bytes(nq));
+  int rc = scan_launch(D, doclen, Nd, Ld, dim, Q, nq, Lq, S, Nd, ws, stream);
+  if (rc) return rc;
+  return launch_topk_select(S, Nd, nq, Nd, k, id_base, nullptr, out_score, out_id, stream);
+}

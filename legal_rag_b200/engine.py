@@ -207,6 +207,50 @@ def maxsim_rerank(D, doclen, Q, cand, k: int, id_base: int = 0):
     return s, i
 
 
+def maxsim_scan_supported(Ld: int) -> bool:
+    """Token-store row lengths the batched full-corpus kernel takes (documents must tile its 256-row block)."""
+    return Ld in (32, 64, 128, 256)
+
+
+def maxsim_scan_scores(D: torch.Tensor, doclen: Optional[torch.Tensor], Q: torch.Tensor) -> torch.Tensor:
+    """MaxSim of every document against every query of the batch: D [Nd, Ld, 128] bf16, Q [nq, Lq, 128] bf16
+    -> [nq, Nd] float32.  One tensor-core contraction; the token store is read once per batch."""
+    lib = _native.init(D.device.index)
+    D = _need(D, torch.bfloat16, 3, "D")
+    Q = _need(Q, torch.bfloat16, 3, "Q")
+    if doclen is not None:
+        doclen = _need(doclen, torch.int32, 1, "doclen")
+    Nd, Ld, dim = D.shape
+    nq, Lq, _ = Q.shape
+    out = torch.empty((nq, Nd), dtype=torch.float32, device=D.device)
+    ws = _ws(lib.lrag_maxsim_scan_workspace_bytes(Nd, nq, 0), D.device)
+    check(lib.lrag_maxsim_scan_scores_bf16(_ptr(D), _ptr(doclen), Nd, Ld, dim, _ptr(Q), nq, Lq, _ptr(out), Nd, _ptr(ws), ws.numel(),
+                                           _stream()), "lrag_maxsim_scan_scores_bf16")
+    return out
+
+
+def maxsim_scan_topk(D: torch.Tensor, doclen: Optional[torch.Tensor], Q: torch.Tensor, k: int, id_base: int = 0,
+                     max_score_bytes: int = 1 << 30):
+    """Exact full-corpus MaxSim top-k for a query batch; queries are processed in groups whose [group, Nd] score
+    matrix stays under `max_score_bytes`."""
+    lib = _native.init(D.device.index)
+    D = _need(D, torch.bfloat16, 3, "D")
+    Q = _need(Q, torch.bfloat16, 3, "Q")
+    if doclen is not None:
+        doclen = _need(doclen, torch.int32, 1, "doclen")
+    Nd, Ld, dim = D.shape
+    nq, Lq, _ = Q.shape
+    s, i = _out(nq, k, D.device)
+    group = max(4, min(nq, (max_score_bytes // (4 * Nd)) // 4 * 4))
+    ws = _ws(lib.lrag_maxsim_scan_workspace_bytes(Nd, min(group, nq), k), D.device)
+    for q0 in range(0, nq, group):
+        n = min(group, nq - q0)
+        rc = lib.lrag_maxsim_scan_topk_bf16(_ptr(D), _ptr(doclen), Nd, Ld, dim, _ptr(Q[q0:q0 + n]), n, Lq, k, id_base,
+                                            _ptr(s[q0:q0 + n]), _ptr(i[q0:q0 + n]), _ptr(ws), ws.numel(), _stream())
+        check(rc, "lrag_maxsim_scan_topk_bf16")
+    return s, i
+
+
 # ------------------------------------------------------------------------------------------------
 # fusion
 # ------------------------------------------------------------------------------------------------
@@ -250,7 +294,7 @@ def fuse_topk(dense=None, bm25=None, colbert=None, *, k: int, method: str = "rrf
 # ------------------------------------------------------------------------------------------------
 # launch profiler (bench.py's roofline leg)
 # ------------------------------------------------------------------------------------------------
-PROF_TAGS = {0: "dense_scan", 1: "bm25_scan", 2: "maxsim", 3: "fuse"}
+PROF_TAGS = {0: "dense_scan", 1: "bm25_scan", 2: "maxsim", 3: "fuse", 4: "select", 5: "maxsim_scan"}
 
 
 def prof_enable(capacity: int) -> None:

@@ -436,3 +436,36 @@ def test_gather_scores_match_numpy(eng, N, d, nq, C):
     ok = (rows >= 0) & (rows < N)
     np.testing.assert_allclose(got[ok], want[ok], rtol=1e-4, atol=1e-5)
     assert np.isneginf(got[~ok]).all()
+
+
+# ---------------------------------------------------------------- batched full-corpus MaxSim
+@pytest.mark.parametrize("Nd,Ld,Lq,nq,k", [(700, 128, 32, 9, 100), (1000, 64, 7, 4, 10), (333, 32, 32, 5, 20), (97, 256, 20, 3, 50),
+                                            (5000, 128, 32, 64, 100)])
+def test_maxsim_scan_matches_oracle(eng, Nd, Ld, Lq, nq, k):
+    rng = np.random.default_rng(Nd + Ld + nq)
+    Dd, Dr = _bf16(_unit(rng, (Nd, Ld, 128)))
+    Qd, Qr = _bf16(_unit(rng, (nq, Lq, 128)))
+    doclen = rng.integers(1, Ld + 1, Nd).astype(np.int32)
+    doclen[:5] = Ld
+    doclen[5] = 0                                          # an empty document scores Lq * -9999
+    cand = np.tile(np.arange(Nd, dtype=np.int64), (nq, 1))
+    want = omaxsim.maxsim_scores(Qr, Dr, doclen, cand)
+    got = eng.maxsim_scan_scores(Dd, torch.from_numpy(doclen).cuda(), Qd).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-4)
+    # no doclen array = every document is full length
+    got_full = eng.maxsim_scan_scores(Dd, None, Qd).cpu().numpy()
+    np.testing.assert_allclose(got_full, omaxsim.maxsim_scores(Qr, Dr, None, cand), rtol=2e-4, atol=2e-4)
+    # ranked, in query groups small enough to force several launches; equals the gather kernel on all candidates
+    s, i = eng.maxsim_scan_topk(Dd, torch.from_numpy(doclen).cuda(), Qd, k, id_base=11, max_score_bytes=4 * Nd * 8)
+    O_s, O_i = omaxsim.rerank_topk(Qr, Dr, doclen, cand, min(k + 10, Nd))
+    check_topk_parity(s.cpu().numpy(), i.cpu().numpy() - 11 * (i.cpu().numpy() >= 0), O_s, O_i, k, 1e-4, what="maxsim-scan", floor=1.0)
+    s2, i2 = eng.maxsim_rerank(Dd, torch.from_numpy(doclen).cuda(), Qd, torch.from_numpy(cand).cuda(), k, id_base=11)
+    check_topk_parity(s.cpu().numpy(), i.cpu().numpy(), s2.cpu().numpy(), i2.cpu().numpy(), min(k, Nd), 1e-5, what="scan-vs-gather", floor=1.0)
+
+
+def test_maxsim_scan_rejects_row_lengths_that_do_not_tile(eng):
+    D = torch.zeros((10, 96, 128), dtype=torch.bfloat16, device="cuda")
+    Q = torch.zeros((2, 32, 128), dtype=torch.bfloat16, device="cuda")
+    assert not eng.maxsim_scan_supported(96)
+    with pytest.raises(Exception, match="must be 32, 64, 128 or 256"):
+        eng.maxsim_scan_scores(D, None, Q)
