@@ -33,14 +33,16 @@ def _bf16_bits(x: np.ndarray) -> np.ndarray:
 
 def build_token_store(cfg, chunks: Sequence[LawChunk], encoder=None) -> Path:
     """Offline counterpart of builders/colbert_builder.py:55-136 for this engine: encode every chunk to
-    unit 128-d token vectors, pad to a common length (multiple of 16, <= 256) and save bf16 bits + lengths."""
+    unit 128-d token vectors, pad to a common length (32, 64, 128 or 256 rows: lengths that tile the 256-row
+    block of the batched full-corpus scan) and save bf16 bits + lengths."""
     rcfg = cfg.retrieval
     enc = encoder or encoders.make_token_encoder(str(rcfg.colbert_model_name), "cpu")
     mats = [np.asarray(enc.encode_doc((c.text or "").strip()), dtype=np.float32)[: int(getattr(rcfg, "colbert_doc_maxlen", 220))]
             for c in chunks]
-    Ld = max(16, int(-(-max(m.shape[0] for m in mats) // 16) * 16))
-    if Ld > 256:
-        raise ValueError(f"documents of {Ld} tokens exceed the 256-token tile of the MaxSim kernel")
+    longest = max(m.shape[0] for m in mats)
+    if longest > 256:
+        raise ValueError(f"documents of {longest} tokens exceed the 256-token tile of the MaxSim kernel")
+    Ld = next(n for n in (32, 64, 128, 256) if n >= longest)
     toks = np.zeros((len(mats), Ld, DIM), dtype=np.float32)
     doclen = np.zeros(len(mats), dtype=np.int32)
     for i, m in enumerate(mats):
@@ -129,6 +131,9 @@ class ColBERTRetriever:
         Nd = self._tokens.shape[0]
         k = max(1, min(int(top_k), Nd, engine.LRAG_MAX_K))
         Q = self._encode_queries(queries)
+        if Q.shape[0] > 1 and engine.maxsim_scan_supported(int(self._tokens.shape[1])):
+            # a batch shares one pass over the token store (tensor-bound contraction) instead of one gather per query
+            return engine.maxsim_scan_topk(self._tokens, self._doclen, Q, k)
         cand = torch.arange(Nd, device=self.device, dtype=torch.int64).unsqueeze(0).expand(Q.shape[0], Nd).contiguous()
         return engine.maxsim_rerank(self._tokens, self._doclen, Q, cand, k)
 
