@@ -14,6 +14,8 @@
 // similarity matrices never leave TMEM; what is written is the [nq, Nd] per-document score matrix
 // (1/4096 of the token-level products), ranked by lrag_topk_select_f32.
 // Arithmetic intensity = nq * 32 / ... >= 2048 FLOP per store byte at 64 queries: tensor-bound.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "select.cuh"
 
@@ -40,6 +42,7 @@ struct ScanParams {
   int Ld, Lq, nq, QB;
   int64_t DT;          // doc tiles
   int P, L;            // P query blocks are in flight at a time, L CTAs share each of them
+  int debug;           // timing experiments: 1 = epilogue reads nothing (accumulators handed straight back)
 };
 
 // Work split: CTA c serves query block (pass * P + c % P) in pass `pass` and takes the doc tiles
@@ -162,7 +165,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
         float m = SC_PAD_FILL;
 #pragma unroll 1
-        for (int c = half * (SC_BN / 64); c < (half + 1) * (SC_BN / 64); ++c) {
+        for (int c = half * (SC_BN / 64); c < (p.debug == 1 ? 0 : (half + 1) * (SC_BN / 64)); ++c) {
           const int col = c * 32;
           const int din = col / p.Ld, off = col - din * p.Ld;
           const int dl = __shfl_sync(0xffffffffu, dl_mine, din);
@@ -238,6 +241,7 @@ static int scan_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld,
   ScanParams p;
   p.doclen = doclen; p.out = out; p.Nd = Nd; p.ld_out = ld_out; p.Ld = Ld; p.Lq = Lq; p.nq = nq;
   p.QB = (nq + 3) / 4;
+  { const char* dbg = getenv("LRAG_SCAN_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
   p.DT = (Nd * Ld + SC_BN - 1) / SC_BN;
   // queries as 32-row blocks: [nq, Lq, 128] -> zero-padded [QB * 4, 32, 128] (in-bounds TMA boxes, zero rows add 0)
   LRAG_CHECK_CUDA(cudaMemsetAsync(qpad, 0, scan_qpad_bytes(nq), stream));
