@@ -130,7 +130,7 @@ int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
 /* Tuning knob (process-wide; call before sizing the workspace): documents per work item =
  * slabs * 16384.  Small items keep the posting ranges all queries are working on inside L2;
- * large items amortise the per-item state hand-off.  0 restores the default (8, or the
+ * large items amortise the per-item state hand-off.  0 restores the default (32, or the
  * LRAG_BM25_ITEM_SLABS environment variable). */
 int lrag_bm25_set_item_slabs(int slabs);
 int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,

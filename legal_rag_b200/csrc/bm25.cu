@@ -64,7 +64,7 @@ constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the 
 constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
-constexpr int BM25_DEFAULT_ITEM_SLABS = 16;
+constexpr int BM25_DEFAULT_ITEM_SLABS = 32;
 constexpr int BM25_GATHER_MAX = 64;                  // runs this short share one ring stage (32 runs x 64 postings fill it at most)
 static_assert(32 * BM25_GATHER_MAX <= BM25_CHUNK, "a gather stage must hold one lane batch of short runs");
 enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
@@ -772,11 +772,18 @@ static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int
   pl.cap = 2 * pl.P < 512 ? 512 : 2 * pl.P;         // <= 2048 = 4 * BM25_CONSUMERS
   pl.TS = int(max_query_terms < 1 ? 1 : (max_query_terms > BM25_MAXT ? BM25_MAXT : max_query_terms));
   pl.item_slabs = bm25_item_slabs();
+  // few queries: split every query's doc range into independent chains so that the machine is full, with items
+  // small enough that there is about one chain per resident CTA (equal doc ranges of one query are equal work)
+  const int64_t resident = 2 * int64_t(sms);
+  if (nq < 2 * resident) {
+    const int64_t nslab = (N + BM25_SLAB - 1) / BM25_SLAB;
+    int64_t want = (nslab * nq + resident - 1) / resident;
+    if (want < 1) want = 1;
+    if (want < pl.item_slabs) pl.item_slabs = int(want);
+  }
   const int64_t item_docs = int64_t(pl.item_slabs) * BM25_SLAB;
   int64_t n_items = (N + item_docs - 1) / item_docs;
   if (n_items < 1) n_items = 1;
-  // few queries: split every query's doc range into independent chains so that the machine is full
-  const int64_t resident = 2 * int64_t(sms);
   int64_t S = 1;
   if (nq < 2 * resident) { S = (2 * resident + nq - 1) / nq; if (S > n_items) S = n_items; }
   const int64_t items_per_split = (n_items + S - 1) / S;
