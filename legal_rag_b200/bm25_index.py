@@ -126,6 +126,9 @@ class Bm25HostIndex:
         from .engine import Bm25DeviceIndex
         hi = self.n_docs if hi is None else hi
         imp = self.impacts()
+        # one bound for every shard of the corpus: the fixed-point scale of a query, and with it every score bit,
+        # is then the same whichever way the corpus is sharded
+        bound = float(np.abs(imp).max()) if imp.size else 0.0
         if lo == 0 and hi == self.n_docs:
             indptr, doc_id = self.indptr, self.doc_id
         else:
@@ -139,7 +142,7 @@ class Bm25HostIndex:
         nonneg = bool((imp >= 0).all()) if imp.size else True
         return Bm25DeviceIndex(torch.from_numpy(np.ascontiguousarray(indptr)).to(device),
                                torch.from_numpy(np.ascontiguousarray(doc_id)).to(device),
-                               torch.from_numpy(np.ascontiguousarray(imp)).to(device), hi - lo, nonneg, lo)
+                               torch.from_numpy(np.ascontiguousarray(imp)).to(device), hi - lo, nonneg, lo, bound)
 
     # ------------------------------------------------------------------ queries
     def encode_queries(self, queries: Sequence[Sequence]) -> Tuple[np.ndarray, np.ndarray, int]:
