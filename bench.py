@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|maxsim_scan|bm25|hybrid]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|maxsim_scan|bm25|hybrid|ucc]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
@@ -514,7 +514,109 @@ class MaxsimScanWorkload:
         return run, f"oracle numpy-fp32 MaxSim of {nq_s} queries against {n_s} documents per step, extrapolated linearly in documents to {self.Nd}"
 
 
-WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "maxsim_scan": MaxsimScanWorkload, "bm25": Bm25Workload, "hybrid": HybridWorkload}
+class UccWorkload:
+    """BASELINE.json configs[0]: the UCC article corpus (591 docs, vocabulary 3926, 53 991 postings) with random unit
+    768-d embeddings, 1024 synthetic queries (random unit vectors + windows of 3-8 consecutive tokens of a random doc), dense + BM25
+    top-100 and weighted fusion 0.6/0.4.  Small enough for the literal oracle: this is the CPU-runnable case."""
+    name = "ucc_hybrid"
+    dtype = "bf16"
+    dominant = "dense_scan"
+
+    def __init__(self, args, rank, world, device):
+        self.nq, self.k = args.nq or 1024, args.k
+        self.rank, self.world, self.device = rank, world, device
+
+    def _corpus(self):
+        import numpy as np
+        z = np.load(os.path.join(ROOT, "tests", "golden", "ucc_corpus.npz"))
+        lens, flat = z["doc_len"].astype(np.int64), z["tokens"].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)])
+        docs = [flat[off[i]:off[i + 1]] for i in range(len(lens))]
+        X = np.random.default_rng(42).standard_normal((len(docs), 768)).astype(np.float32)
+        X /= np.linalg.norm(X, axis=1, keepdims=True)
+        Q = np.random.default_rng(43).standard_normal((self.nq, 768)).astype(np.float32)
+        Q /= np.linalg.norm(Q, axis=1, keepdims=True)
+        rng = np.random.default_rng(44)
+        queries = []
+        for _ in range(self.nq):
+            d = docs[int(rng.integers(0, len(docs)))]
+            L = int(rng.integers(3, 9))
+            st = int(rng.integers(0, max(1, len(d) - L)))
+            queries.append(d[st:st + L].tolist())
+        return docs, int(len(z["vocab"])), X, Q, queries
+
+    def config(self):
+        return {"workload": f"configs[0] UCC corpus hybrid (dense flat-IP + BM25 + weighted_sum 0.6/0.4), 591 docs, {self.nq} queries, top-{self.k}",
+                "l2": "whole corpus fits in L2: this configuration measures launch and host latency, not bandwidth", "parallelism": "single GPU"}
+
+    def setup(self):
+        import torch
+        from legal_rag_b200 import engine
+        from legal_rag_b200.bm25_index import Bm25HostIndex
+        self.torch, self.engine = torch, engine
+        docs, V, X, Q, queries = self._corpus()
+        self.N = len(docs)
+        self.kk = min(self.k, self.N)
+        self.X = torch.from_numpy(X).to(self.device).to(torch.bfloat16)
+        self.Q = torch.from_numpy(Q).to(self.device).to(torch.bfloat16)
+        host = Bm25HostIndex.from_token_ids(docs, V)
+        self.index = host.to_device(self.device)
+        qi, qt, self.mx = host.encode_queries(queries)
+        self.qi, self.qt = torch.from_numpy(qi).to(self.device), torch.from_numpy(qt).to(self.device)
+        self.host = [self.Q.cpu().pin_memory(), self.qi.cpu().pin_memory(), self.qt.cpu().pin_memory()]
+
+    def _search(self, Q, qi, qt):
+        eng = self.engine
+        d = eng.dense_topk(self.X, Q, self.kk)
+        b = eng.bm25_topk(self.index, qi, qt, self.mx, self.kk)
+        return eng.fuse_topk(d, b, None, k=self.kk, method="weighted_sum", w_dense=0.6, w_bm25=0.4)
+
+    def step(self):
+        return self._search(self.Q, self.qi, self.qt)
+
+    def e2e_step(self):
+        Q, qi, qt = (t.to(self.device, non_blocking=True) for t in self.host)
+        s, i = self._search(Q, qi, qt)
+        return s.cpu(), i.cpu()
+
+    def e2e_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.host), self.nq * self.kk * 12
+
+    def units_per_step(self):
+        return self.nq * self.world
+
+    def roofline(self, kernel_ms, peaks):
+        flops = 2.0 * self.nq * self.N * 768
+        ach = flops / (max(kernel_ms, 1e-6) * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "traffic": None, "kernel": "dense_scan_kernel (591 docs: three doc tiles; the step is launch-latency bound)", "kernel_ms": kernel_ms,
+                "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per step", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+
+    def cpu_sample(self, budget_s=15.0):
+        """The reference's path in full on this corpus: numpy fp32 flat-IP, literal BM25Okapi.get_scores + stable sort, _fuse."""
+        import numpy as np
+        from oracle import bm25 as obm25, dense as odense, fuse as ofuse
+        docs, V, X, Q, queries = self._corpus()
+        lit = obm25.BM25Okapi([[str(t) for t in d] for d in docs])
+        nq_s = 64
+        kk = min(self.k, len(docs))
+
+        def run():
+            t0 = time.perf_counter()
+            for j in range(nq_s):
+                ds, di = odense.flat_ip_topk(Q[j:j + 1], X, kk)
+                bs, bi = obm25.search(lit, [str(t) for t in queries[j]], kk)
+                ofuse.fuse(list(zip(di[0].tolist(), ds[0].tolist())), list(zip(bi.tolist(), bs.tolist())), [], method="weighted_sum",
+                           w_dense=0.6, w_bm25=0.4)
+            dt = time.perf_counter() - t0
+            return nq_s / dt, dt
+        return run, f"oracle restatement of the reference path on the whole UCC corpus, one query at a time, {nq_s} of the {self.nq} queries per step"
+
+    cpu_cores = 1
+
+
+WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "maxsim_scan": MaxsimScanWorkload, "bm25": Bm25Workload, "hybrid": HybridWorkload,
+             "ucc": UccWorkload}
 
 
 # =================================================================================================

@@ -469,3 +469,28 @@ def test_maxsim_scan_rejects_row_lengths_that_do_not_tile(eng):
     assert not eng.maxsim_scan_supported(96)
     with pytest.raises(Exception, match="must be 32, 64, 128 or 256"):
         eng.maxsim_scan_scores(D, None, Q)
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[0], end to end
+def test_config0_ucc_hybrid_matches_reference_path(eng):
+    """UCC corpus, random unit embeddings (seed 42), 1024 synthetic queries (seeds 43/44), dense + BM25 top-100 and
+    weighted fusion 0.6/0.4 -- every query against the literal oracle pipeline (flat-IP, BM25Okapi.get_scores + stable sort, _fuse)."""
+    import argparse
+    import bench
+    wl = bench.UccWorkload(argparse.Namespace(nq=1024, k=100), 0, 1, torch.device("cuda", 0))
+    wl.setup()
+    s, i = wl.step()
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    docs, V, X, Q, queries = wl._corpus()
+    Xr = torch.from_numpy(X).to(torch.bfloat16).float().numpy()      # the engine's inputs are the bf16-rounded embeddings
+    Qr = torch.from_numpy(Q).to(torch.bfloat16).float().numpy()
+    lit = obm25.BM25Okapi([[str(t) for t in d] for d in docs])
+    for method in ("weighted_sum",):
+        for q in range(0, 1024, 4):
+            ds, di = odense.flat_ip_topk(Qr[q:q + 1], Xr, 100)
+            bs, bi = obm25.search(lit, [str(t) for t in queries[q]], 100)
+            ref = ofuse.fuse(list(zip(di[0].tolist(), ds[0].tolist())), list(zip(bi.tolist(), bs.tolist())), [], method=method,
+                             w_dense=0.6, w_bm25=0.4)
+            m = min(len(ref), 120)
+            check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
+                              100, 2e-3, what=f"config0-{method}")
