@@ -149,3 +149,32 @@ def test_bm25_tiny_corpus_and_k_larger_than_n(eng):
         if dev.nonneg:
             assert got_i[:3].tolist() == oi.tolist(), (toks, got_i, oi)
             np.testing.assert_allclose(got_s[:3], os_, rtol=1e-3, atol=1e-6)
+
+
+def test_bm25_negative_idf_corpus_spanning_slabs_and_items(eng):
+    """Every term occurs in most documents, so rank_bm25's epsilon-floored idf is negative for all of them: matched
+    documents score below untouched ones, no slab may be skipped and zero-score documents are ranked, across several
+    slabs, work items and (with few queries) split chains."""
+    from legal_rag_b200.bm25_index import Bm25HostIndex
+    rng = np.random.default_rng(9)
+    N, V = 40_000, 8
+    docs = [np.nonzero(rng.random(V) < 0.8)[0] for _ in range(N)]
+    docs = [d if d.size else np.array([0]) for d in docs]
+    for j in range(0, N, 97):
+        docs[j] = np.array([V - 1])                 # documents that match few queries keep score 0 often
+    host = Bm25HostIndex.from_token_ids(docs, V)
+    csr = obm25.CsrBM25.from_token_ids(docs, V)
+    dev = host.to_device("cuda")
+    assert not dev.nonneg
+    queries = [[0], [1, 2], [3, 3, 4], [5], [0, 1, 2, 3, 4, 5, 6], [V + 3]]
+    qi, qt, mx = host.encode_queries(queries)
+    for item_slabs, reps in ((0, 1), (1, 120)):
+        eng.bm25_set_item_slabs(item_slabs)
+        try:
+            s, i = eng.bm25_topk(dev, torch.from_numpy(np.concatenate([qi[:-1] + r * qi[-1] for r in range(reps)] + [[reps * qi[-1]]])).cuda(),
+                                 torch.from_numpy(np.tile(qt, reps)).cuda(), mx, 50)
+        finally:
+            eng.bm25_set_item_slabs(0)
+        s, i = s[:len(queries)].cpu().numpy(), i[:len(queries)].cpu().numpy()
+        O = [csr.search(q, 80) for q in queries]
+        check_topk_parity(s, i, np.stack([o[0] for o in O]), np.stack([o[1] for o in O]), 50, 1e-3, what=f"bm25-negidf-items{item_slabs}")
