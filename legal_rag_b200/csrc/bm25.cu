@@ -599,14 +599,22 @@ bm25_scan_kernel(const Bm25Params p) {
         const bool hit = consumers_bar_or(!p.nonneg || float(mx) * inv_scale >= thr_s);
         if (hit) {
           // ---- scan the slab for candidates ----
+          // Coarse filter in the integer domain (no conversion for the ~all accumulators that cannot matter):
+          // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s.
+          int thr_i = INT_MIN;
+          if (thr_s > -INFINITY) {
+            const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
+            thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
+            if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
+          }
           const int4* a4 = reinterpret_cast<const int4*>(acc);
 #pragma unroll 2
           for (int i = 0; i < BM25_SLAB / 4 / BM25_CONSUMERS; ++i) {
             const int idx = (tid + i * BM25_CONSUMERS) * 4;
             const int4 s4 = a4[tid + i * BM25_CONSUMERS];
-            const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
-            const bool any4 = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3])) >= thr_s;
+            const bool any4 = max(max(s4.x, s4.y), max(s4.z, s4.w)) >= thr_i;
             if (!__any_sync(0xffffffffu, any4)) continue;
+            const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int64_t doc = slab0 + idx + e;
