@@ -369,13 +369,24 @@ class HybridShard:
 
     def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
                       Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",
-                      w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, **fuse_kw):
+                      w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, colbert_mode: str = "rerank",
+                      **fuse_kw):
+        """colbert_mode "rerank": MaxSim over the fused candidate union (the north star's rerank).  "scan": ColBERT as a
+        first-stage channel over the whole corpus like the reference (hybrid_retriever.py:299) -- every document of the
+        shard is scored by the batched full-corpus kernel; needs one token row per document (no id aliasing)."""
         import torch.distributed as dist
         ds, di = allgather_merge(*dense_topk(self.X, Qd, kc, self.id_base), kc, self.group)
         bs, bi = allgather_merge(*bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc), kc, self.group)
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, w_colbert=w_colbert, **fuse_kw)
         if self.tokens is None or Qtok is None:
             return fuse_topk((ds, di), (bs, bi), None, k=k, **kw)
+        if colbert_mode == "scan":
+            if self.tokens.shape[0] != self.X.shape[0] or self.tok_row_base != self.id_base:
+                raise LragError("colbert_mode='scan' needs one token row per document of the shard")
+            kk = min(kc, int(self.tokens.shape[0]))
+            cs, ci = maxsim_scan_topk(self.tokens, self.doclen, Qtok, kk, id_base=self.id_base)
+            cs, ci = allgather_merge(cs, ci, kk, self.group)
+            return fuse_topk((ds, di), (bs, bi), (cs, ci), k=k, **kw)
         # candidate set = every doc either channel returned, best fused first; -1 pads short rows
         _, cand_gid = fuse_topk((ds, di), (bs, bi), None, k=2 * kc, method=method, w_dense=w_dense, w_bm25=w_bm25)
         rows = torch.where(cand_gid >= 0, cand_gid % max(1, self.tok_rows_total), cand_gid) - self.tok_row_base

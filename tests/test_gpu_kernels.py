@@ -420,6 +420,20 @@ def test_hybrid_shard_matches_oracle_pipeline(eng):
             m = min(len(ref), k + 8)
             check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
                               k, 2e-3, what=f"hybrid-{method}")
+    # ColBERT as a first-stage channel over the whole corpus (the reference's own arrangement, hybrid_retriever.py:299)
+    s, i = shard.search_device(Qd, torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), mx, Qtd, k=k, kc=kc, method="rrf_norm_blend",
+                               colbert_mode="scan")
+    s, i = s.cpu().numpy(), i.cpu().numpy()
+    all_docs = np.arange(N, dtype=np.int64)[None, :]
+    for q in range(nq):
+        dl = list(zip(I[q].tolist(), D[q].tolist()))
+        bs, bi = csr.search(queries[q], kc)
+        cs = omaxsim.maxsim_scores(Qtr[q:q + 1], Tr, None, all_docs)[0]
+        order = np.lexsort((all_docs[0], -cs.astype(np.float64)))[:kc]
+        ref = ofuse.fuse(dl, list(zip(bi.tolist(), bs.tolist())), [(int(o), float(cs[o])) for o in order], method="rrf_norm_blend")
+        m = min(len(ref), k + 8)
+        check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
+                          k, 2e-3, what="hybrid-colbert-scan")
 
 
 # ---------------------------------------------------------------- gathered inner products (graph-expansion scoring)
