@@ -335,13 +335,17 @@ class HybridWorkload:
     def __init__(self, args, rank, world, device):
         self.N, self.d, self.V = args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
         self.nq, self.k, self.kc = args.nq or 4096, args.k, args.k
-        self.Nd_tok, self.Ld, self.Lq = max(1, self.N // 100), 128, 32
+        self.colbert_mode = getattr(args, "colbert_mode", "rerank")
+        # rerank: configs[4]'s 1M-doc token store (ids aliased onto it); scan: one token row per document of the shard
+        self.Nd_tok, self.Ld, self.Lq = (max(1, self.N // 100), 128, 32) if self.colbert_mode == "rerank" else (self.N, 128, 32)
         self.rank, self.world, self.device = rank, world, device
 
     def config(self):
         return {"workload": f"configs[4] hybrid top-{self.k}: per GPU {self.N} x {self.d} bf16 dense rows + {self.N} BM25 docs (Zipf vocab {self.V}, "
                             f"mean length 24) + {self.Nd_tok} x {self.Ld} x 128 ColBERT token rows; batch {self.nq} queries; per-channel top-{self.kc}, "
-                            f"MaxSim over the fused candidate union (<= {2 * self.kc}), weighted_sum 0.6/0.4/0.35",
+                            + (f"MaxSim over the fused candidate union (<= {2 * self.kc})" if self.colbert_mode == "rerank"
+                               else "ColBERT as a first-stage channel: MaxSim of every document (batched full-corpus scan)")
+                            + ", weighted_sum 0.6/0.4/0.35",
                 "corpus_docs_total": self.N * self.world, "postings": getattr(self, "nnz", None),
                 "token_rows": "global id mod total token rows (synthetic aliasing of the id space onto the token store, SURVEY 8d C5)",
                 "parallelism": (f"doc-sharded x{self.world}: per channel local top-k + NCCL all-gather + merge, MaxSim by row owner + NCCL max-reduce, "
@@ -359,7 +363,8 @@ class HybridWorkload:
         index, st = synth.bm25_synthetic_index(self.N, self.V, 10 + self.rank, self.device, mean_len=24.0, id_base=base)
         self.nnz = st["nnz"]
         tokens = synth.unit_tokens_bf16(self.Nd_tok, self.Ld, 128, 5 + self.rank, self.device)
-        self.shard = engine.HybridShard(X, index, tokens, None, id_base=base, tok_row_base=self.rank * self.Nd_tok,
+        self.shard = engine.HybridShard(X, index, tokens, None, id_base=base,
+                                        tok_row_base=self.rank * self.Nd_tok if self.colbert_mode == "rerank" else base,
                                         tok_rows_total=self.Nd_tok * self.world)
         self.Qd = synth.unit_rows_bf16(self.nq, self.d, 21, self.device, chunk=self.nq)
         self.q_indptr, self.q_term, self.mx = synth.bm25_synthetic_queries(self.nq, self.V, 11, self.device)
@@ -378,10 +383,13 @@ class HybridWorkload:
             marks[1].record()
             b = eng.allgather_merge(*eng.bm25_topk(sh.bm25, self.q_indptr, self.q_term, self.mx, self.kc), self.kc)
             marks[2].record()
-            _, gid = eng.fuse_topk(d, b, None, k=2 * self.kc, method="weighted_sum")
-            rows = torch.where(gid >= 0, gid % sh.tok_rows_total, gid) - sh.tok_row_base
-            own = (gid >= 0) & (rows >= 0) & (rows < sh.tokens.shape[0])
-            eng.maxsim_scores(sh.tokens, None, self.Qtok, torch.where(own, rows, torch.full_like(rows, -1)))
+            if self.colbert_mode == "rerank":
+                _, gid = eng.fuse_topk(d, b, None, k=2 * self.kc, method="weighted_sum")
+                rows = torch.where(gid >= 0, gid % sh.tok_rows_total, gid) - sh.tok_row_base
+                own = (gid >= 0) & (rows >= 0) & (rows < sh.tokens.shape[0])
+                eng.maxsim_scores(sh.tokens, None, self.Qtok, torch.where(own, rows, torch.full_like(rows, -1)))
+            else:
+                eng.allgather_merge(*eng.maxsim_scan_topk(sh.tokens, None, self.Qtok, self.kc, id_base=sh.id_base), self.kc)
             marks[3].record()
             self.step()
             marks[4].record()
@@ -390,10 +398,12 @@ class HybridWorkload:
                           "candidates+maxsim": marks[2].elapsed_time(marks[3]), "whole_step": marks[3].elapsed_time(marks[4])}
 
     def step(self):
-        return self.shard.search_device(self.Qd, self.q_indptr, self.q_term, self.mx, self.Qtok, k=self.k, kc=self.kc)
+        return self.shard.search_device(self.Qd, self.q_indptr, self.q_term, self.mx, self.Qtok, k=self.k, kc=self.kc,
+                                        colbert_mode=self.colbert_mode)
 
     def e2e_step(self):
-        return self.shard.search(self.host[0], self.host[1], self.host[2], self.mx, self.host[3], k=self.k, kc=self.kc)
+        return self.shard.search(self.host[0], self.host[1], self.host[2], self.mx, self.host[3], k=self.k, kc=self.kc,
+                                 colbert_mode=self.colbert_mode)
 
     def e2e_bytes(self):
         return sum(t.numel() * t.element_size() for t in self.host), self.nq * self.k * 12
@@ -656,6 +666,8 @@ def main():
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--mean-len", type=float, default=0.0, help="bm25: mean document length of the synthetic corpus (default 40)")
+    ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
+                    help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
