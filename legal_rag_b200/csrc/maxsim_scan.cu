@@ -41,14 +41,16 @@ struct ScanParams {
   int64_t Nd, ld_out;
   int Ld, Lq, nq, QB;
   int64_t DT;          // doc tiles
-  int P, L;            // P query blocks are in flight at a time, L CTAs share each of them
+  int64_t units;       // work units = QB * nchunks, unit u = (chunk u / QB, query block u % QB)
+  int64_t chunk_tiles; // doc tiles per chunk
   int debug;           // timing experiments: 1 = epilogue reads nothing (accumulators handed straight back)
 };
 
-// Work split: CTA c serves query block (pass * P + c % P) in pass `pass` and takes the doc tiles
-// c / P, c / P + L, ... of it.  The query block stays in shared memory for the whole pass (it is the A operand
-// of every tile), only doc tiles stream; the P CTAs that hold different query blocks walk the doc tiles in step,
-// so a doc tile comes from HBM once and from L2 for the others.
+// Work split: the doc tiles are cut into chunks; unit u = (chunk u / QB, query block u % QB) goes to CTA u mod grid.
+// A unit's query block sits in shared memory (the A operand of every tile of the unit), only doc tiles stream.
+// The QB units of a chunk are consecutive, so they run on neighbouring CTAs at the same time: a doc tile comes from
+// HBM once and from L2 for the other query blocks.  Units are much smaller than a CTA's share (about 64 per CTA), so
+// every query-batch size keeps all SMs busy to within a couple of percent.
 __global__ void __launch_bounds__(SC_THREADS, 1)
 maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, const ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -67,9 +69,6 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int my_slot = blockIdx.x % p.P, my_lane = blockIdx.x / p.P;
-  const bool active = my_lane < p.L;
-  const int passes = (p.QB + p.P - 1) / p.P;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_q);
@@ -87,16 +86,22 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && active) {
+    if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int pass = 0; pass < passes; ++pass) {
-        const int qb = pass * p.P + my_slot;
-        if (qb >= p.QB) break;
-        mbar_wait(aempty_bar, (pass & 1) ^ 1);
-        mbar_arrive_expect_tx(afull_bar, SC_A_BYTES);
-        for (int kb = 0; kb < SC_KB; ++kb)
-          tma_load_2d(smem_a + kb * (SC_BM * SC_BK * 2), &tmap_q, afull_bar, kb * SC_BK, qb * SC_BM);
-        for (int64_t dt = my_lane; dt < p.DT; dt += p.L) {
+      int cur_qb = -1; uint32_t a_uses = 0;
+      for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int qb = int(u % p.QB);
+        const int64_t dt0 = (u / p.QB) * p.chunk_tiles;
+        const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
+        if (qb != cur_qb) {
+          // the MMA thread commits aempty when it reaches this unit: every MMA that read the old block has retired
+          mbar_wait(aempty_bar, a_uses & 1);
+          mbar_arrive_expect_tx(afull_bar, SC_A_BYTES);
+          for (int kb = 0; kb < SC_KB; ++kb)
+            tma_load_2d(smem_a + kb * (SC_BM * SC_BK * 2), &tmap_q, afull_bar, kb * SC_BK, qb * SC_BM);
+          cur_qb = qb; ++a_uses;
+        }
+        for (int64_t dt = dt0; dt < dt1; ++dt) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sb = smem_b + stage * SC_B_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], SC_B_BYTES);
@@ -108,16 +113,23 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && active) {
+    if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_BN);
       int stage = 0; uint32_t phase = 0;
       uint32_t it = 0;
-      for (int pass = 0; pass < passes; ++pass) {
-        if (pass * p.P + my_slot >= p.QB) break;
-        mbar_wait(afull_bar, pass & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a);
-        for (int64_t dt = my_lane; dt < p.DT; dt += p.L, ++it) {
+      int cur_qb = -1; uint32_t a_uses = 0;
+      const uint32_t a_addr = smem_u32(smem_a);
+      for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int qb = int(u % p.QB);
+        const int64_t dt0 = (u / p.QB) * p.chunk_tiles;
+        const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
+        if (qb != cur_qb) {
+          umma_commit(aempty_bar);                   // fires once every MMA issued so far has retired
+          mbar_wait(afull_bar, a_uses & 1);
+          tc_fence_after();
+          cur_qb = qb; ++a_uses;
+        }
+        for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
           const uint32_t as = it & 1, aphase = (it >> 1) & 1;
           mbar_wait(&tempty_bar[as], aphase ^ 1);
           mbar_wait(&full_bar[stage], phase);
@@ -136,10 +148,9 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
           umma_commit(&tfull_bar[as]);
           if (++stage == SC_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(aempty_bar);                   // the query block may be replaced once these MMAs retire
       }
     }
-  } else if (active) {
+  } else {
     // ===================== epilogue: max over a document's tokens, sum over the query's tokens =====
     // Two warps per TMEM lane quadrant (= query inside the block); each takes one half of the tile's
     // columns.  With Ld = 256 the single document spans both halves: the partial maxima meet in smem.
@@ -147,11 +158,12 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const int half = (warp - 2) >> 2;
     const int dpt = SC_BN / p.Ld;                  // documents per tile
     uint32_t it = 0;
-    for (int pass = 0; pass < passes; ++pass) {
-      const int qb = pass * p.P + my_slot;
-      if (qb >= p.QB) break;
+    for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const int qb = int(u % p.QB);
+      const int64_t dt0 = (u / p.QB) * p.chunk_tiles;
+      const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
       const int q = qb * 4 + quad;
-      for (int64_t dt = my_lane; dt < p.DT; dt += p.L, ++it) {
+      for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
         const int64_t doc0 = dt * dpt;
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
         // document lengths of the tile, fetched before the accumulator is waited for
@@ -258,11 +270,12 @@ static int scan_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld,
     attr_set = true;
   }
   const int sms = sm_count();
-  p.P = p.QB < sms ? p.QB : sms;                                       // query blocks in flight
-  int64_t L = sms / p.P;                                               // CTAs per query block
-  if (L > p.DT) L = p.DT;
-  p.L = int(L < 1 ? 1 : L);
-  const int grid = p.P * p.L;
+  int64_t nchunks = (int64_t(sms) * 64 + p.QB - 1) / p.QB;             // about 64 units per CTA
+  if (nchunks > p.DT) nchunks = p.DT;
+  p.chunk_tiles = (p.DT + nchunks - 1) / nchunks;
+  nchunks = (p.DT + p.chunk_tiles - 1) / p.chunk_tiles;
+  p.units = nchunks * p.QB;
+  const int grid = int(p.units < sms ? p.units : sms);
   prof_begin(stream, PROF_MAXSIM_SCAN);
   maxsim_scan_kernel<<<grid, SC_THREADS, SC_SMEM, stream>>>(tq, td, p);
   prof_end(stream);
