@@ -176,29 +176,41 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
         float m = SC_PAD_FILL;
-#pragma unroll 1
-        for (int c = half * (SC_BN / 64); c < (p.debug == 1 ? 0 : (half + 1) * (SC_BN / 64)); ++c) {
-          const int col = c * 32;
-          const int din = col / p.Ld, off = col - din * p.Ld;
-          const int dl = __shfl_sync(0xffffffffu, dl_mine, din);
+        // the next chunk's TMEM load is in flight while this one is reduced
+        uint32_t v[2][32];
+        const int c0 = half * (SC_BN / 64);
+        int dl_c[SC_BN / 64], off_c[SC_BN / 64], din_c[SC_BN / 64];
+#pragma unroll
+        for (int i = 0; i < SC_BN / 64; ++i) {
+          const int col = (c0 + i) * 32;
+          din_c[i] = col / p.Ld;
+          off_c[i] = col - din_c[i] * p.Ld;
+          dl_c[i] = p.debug == 1 ? 0 : __shfl_sync(0xffffffffu, dl_mine, din_c[i]);
+        }
+        if (off_c[0] < dl_c[0]) tmem_ld_32x32(taddr + c0 * 32, v[0]);
+#pragma unroll
+        for (int i = 0; i < SC_BN / 64; ++i) {
+          const int c = c0 + i;
+          const int din = din_c[i], off = off_c[i], dl = dl_c[i];
+          tmem_ld_wait();
+          if (i + 1 < SC_BN / 64 && off_c[i + 1 < SC_BN / 64 ? i + 1 : i] < dl_c[i + 1 < SC_BN / 64 ? i + 1 : i])
+            tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
           if (off < dl) {                            // warp-uniform: the chunk holds unmasked tokens
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + col, v);
-            tmem_ld_wait();
+            const uint32_t* vv = v[i & 1];
             if (off + 32 <= dl) {
               float m4[4];
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                float x = __uint_as_float(v[g * 8]);
+                float x = __uint_as_float(vv[g * 8]);
 #pragma unroll
-                for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(v[g * 8 + j]));
+                for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(vv[g * 8 + j]));
                 m4[g] = x;
               }
               m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (off + j < dl) m = fmaxf(m, __uint_as_float(v[j]));
+                if (off + j < dl) m = fmaxf(m, __uint_as_float(vv[j]));
             }
           }
           const bool doc_ends = off + 32 == p.Ld;
