@@ -1,6 +1,7 @@
 // liblrag runtime glue: device binding, error reporting, TMA descriptor encoding.
 #include "common.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 
@@ -47,8 +48,8 @@ static cudaEvent_t* g_prof_ev = nullptr;   // [2 * cap]
 static int* g_prof_tag = nullptr;
 static int g_prof_cap = 0, g_prof_n = 0;
 static bool g_prof_open = false;
-static long long g_launches = 0;
-void note_launch(int n) { g_launches += n; }
+static std::atomic<long long> g_launches{0};     // entry points may be called from several host threads
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void prof_begin(cudaStream_t stream, int tag) {
   if (!g_prof_cap || g_prof_n >= g_prof_cap) return;
@@ -90,7 +91,7 @@ extern "C" int lrag_prof_collect(float* ms, int* tag, int max_n) {
   return n;
 }
 
-extern "C" long long lrag_launch_count(void) { return g_launches; }
+extern "C" long long lrag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int lrag_version(void) { return LRAG_VERSION; }
 extern "C" const char* lrag_last_error(void) { return g_err; }
 extern "C" int lrag_sm_count(void) { return g_sm_count; }

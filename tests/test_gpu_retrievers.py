@@ -207,3 +207,55 @@ def test_graph_retriever_scoring_matches_reference_golden(golden_dir, tmp_path):
                 assert h.score_breakdown["relation_weight"] == b["relation_weight"] and h.score_breakdown["edge_conf"] == b["edge_conf"]
                 assert h.score_breakdown["graph_depth"] == b["graph_depth"]
                 assert h.score_breakdown["semantic"] == pytest.approx(b["semantic"], abs=5e-3)     # bf16 corpus rows
+
+
+def test_engine_is_reentrant_across_host_threads():
+    """SURVEY 8b threading: `search` is called concurrently from Starlette's thread pool.  Four host threads, each on its
+    own CUDA stream, hammer the three channel kernels; every result must equal the single-threaded one."""
+    import threading
+    from legal_rag_b200 import engine
+    from legal_rag_b200.bm25_index import Bm25HostIndex
+    rng = np.random.default_rng(21)
+    N, d, V, nq = 30_000, 256, 2000, 24
+    X = torch.from_numpy(rng.standard_normal((N, d)).astype(np.float32)).cuda().to(torch.bfloat16)
+    Q = torch.from_numpy(rng.standard_normal((nq, d)).astype(np.float32)).cuda().to(torch.bfloat16)
+    docs = [rng.integers(0, V, int(rng.integers(5, 40))) for _ in range(N)]
+    host = Bm25HostIndex.from_token_ids(docs, V)
+    dev = host.to_device("cuda")
+    qi, qt, mx = host.encode_queries([rng.integers(0, V, 5).tolist() for _ in range(nq)])
+    qi, qt = torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda()
+    T = torch.from_numpy(rng.standard_normal((2000, 64, 128)).astype(np.float32)).cuda().to(torch.bfloat16)
+    Qt = torch.from_numpy(rng.standard_normal((nq, 16, 128)).astype(np.float32)).cuda().to(torch.bfloat16)
+    cand = torch.from_numpy(rng.integers(0, 2000, (nq, 300))).cuda()
+
+    def once():
+        a = engine.dense_topk(X, Q, 50)
+        b = engine.bm25_topk(dev, qi, qt, mx, 50)
+        c = engine.maxsim_scores(T, None, Qt, cand)
+        f = engine.fuse_topk(a, b, None, k=50, method="rrf")
+        return [t.clone() for t in (*a, *b, c, *f)]
+
+    want = once()
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(seed):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for _ in range(15):
+                    got = once()
+                    stream.synchronize()
+                    for g, w in zip(got, want):
+                        if not torch.equal(g, w):
+                            errors.append(f"thread {seed}: result differs")
+                            return
+        except Exception as e:       # noqa: BLE001
+            errors.append(f"thread {seed}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
