@@ -4,7 +4,8 @@ The reference delegates to Stanford ColBERT's PLAID Searcher (centroid pruning +
 channel is an EXACT MaxSim scan of a bf16 token store resident in HBM (liblrag maxsim kernel): at the
 reference's corpus sizes (10^3 docs) a full scan is microseconds, and exact MaxSim is what PLAID
 approximates.  The token store is this engine's own artifact, written next to the reference's
-colbert_meta.jsonl by `build_token_store`; reading PLAID index directories is future work."""
+colbert_meta.jsonl by `build_token_store`; when it is absent but the directory holds a PLAID index written by
+colbert's Indexer, that index is decompressed into the same store at load time (retrieval/plaid.py)."""
 from __future__ import annotations
 
 from pathlib import Path
@@ -15,7 +16,7 @@ import torch
 
 from .. import engine
 from ..schemas import LawChunk
-from . import artifacts, encoders
+from . import artifacts, encoders, plaid
 
 TOKEN_STORE_FILE = "lrag_token_store.npz"
 QUERY_MAXLEN = 32
@@ -108,6 +109,14 @@ class ColBERTRetriever:
     def _load_token_store(self) -> None:
         path = token_store_path(self.cfg.retrieval)
         if not path.exists():
+            if plaid.is_plaid_dir(path.parent):
+                # an index written by colbert's Indexer (builders/colbert_builder.py:109-134): decompress it once
+                mtime = (path.parent / "metadata.json").stat().st_mtime
+                if self._store_mtime == mtime and self._tokens is not None:
+                    return
+                toks, doclen = plaid.read_plaid_index(path.parent, self.device)
+                self._tokens, self._doclen, self._store_mtime = toks, doclen, mtime
+                return
             raise RuntimeError(f"ColBERT token store not found: {path}. Run legal_rag_b200.retrieval.build_token_store() first.")
         mtime = path.stat().st_mtime
         if self._store_mtime == mtime and self._tokens is not None:

@@ -259,3 +259,31 @@ def test_engine_is_reentrant_across_host_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_colbert_retriever_serves_a_plaid_directory(world, tmp_path):
+    """No lrag token store, but a PLAID index directory at the reference's path: it is decompressed at load time and
+    searched; scores are the exact MaxSim of the decompressed (4-bit) vectors, as colbert's Searcher would rank them."""
+    import copy
+    from legal_rag_b200.retrieval import ColBERTRetriever, artifacts, plaid
+    from legal_rag_b200.retrieval.colbert_retriever import token_store_path
+    cfg = copy.deepcopy(world["cfg"])
+    chunks, tok_enc = world["chunks"][:120], world["tok_enc"]
+    cfg.retrieval.colbert_index_path = str(tmp_path / "colbert")
+    cfg.retrieval.colbert_meta_file = str(tmp_path / "colbert" / "colbert_meta.jsonl")
+    d = token_store_path(cfg.retrieval).parent
+    docs = [np.asarray(tok_enc.encode_doc(c.text), dtype=np.float32)[:96] for c in chunks]
+    plaid.write_plaid_index(d, docs, n_centroids=256, nbits=4, chunk_docs=50)
+    artifacts.write_colbert_meta(cfg.retrieval.colbert_meta_file, chunks)
+    ColBERTRetriever._instances_by_key.clear()
+    r = ColBERTRetriever.from_config(cfg)
+    tokens, doclen = plaid.read_plaid_index(d)
+    for qn in QUESTIONS[:3]:
+        hits = r.search(qn, 10)
+        assert len(hits) == 10
+        Q = np.asarray(tok_enc.encode_query(qn), dtype=np.float32)[:32][None]
+        Qr = torch.from_numpy(Q).to(torch.bfloat16).float().numpy()
+        O_s, O_i = omaxsim.rerank_topk(Qr, tokens.float().numpy(), doclen.numpy(), np.arange(len(chunks))[None, :], 20)
+        row = {c.id: i for i, c in enumerate(chunks)}
+        check_topk_parity(np.array([[s for _, s in hits]]), np.array([[row[c.id] for c, _ in hits]]), O_s, O_i, 10, 1e-3,
+                          what="plaid", floor=1.0)
