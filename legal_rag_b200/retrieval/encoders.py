@@ -70,6 +70,54 @@ class HashingTokenEncoder:
         return np.stack([self._tok(t) for t in toks])
 
 
+BGE_QUERY_INSTRUCTION = "为这个法律问题生成表示以用于检索相关法律条文："        # vector_store.py:72 (used for both languages)
+
+
+class TransformersBgeEncoder:
+    """BGE-style dense encoder on the same GPU as the index, for installs that have the checkpoint on
+    disk and `transformers` but not FlagEmbedding.  Same observable behaviour as FlagModel as the reference configures it
+    (vector_store.py:66-77, 131-155): [CLS] pooling, L2-normalised float32 vectors, the retrieval instruction prepended
+    to queries only, max_length 512, fp16 weights on a GPU.  `encode_device` / `encode_queries_device` return the vectors
+    as a device tensor, so a query goes from text to the scan kernel without a host round trip.  The transformer forward
+    itself is library code (HF transformers); nothing here is on the accelerated path."""
+
+    def __init__(self, model_path: str, device="cpu", query_instruction: str = BGE_QUERY_INSTRUCTION, use_fp16: Optional[bool] = None):
+        import torch
+        from transformers import AutoModel, AutoTokenizer
+        self.device = torch.device(device)
+        self.query_instruction = query_instruction
+        self.tokenizer = AutoTokenizer.from_pretrained(model_path, local_files_only=True)
+        model = AutoModel.from_pretrained(model_path, local_files_only=True)
+        if use_fp16 is None:
+            use_fp16 = self.device.type == "cuda"
+        self.model = (model.half() if use_fp16 else model.float()).to(self.device).eval()
+        self.dim = int(self.model.config.hidden_size)
+
+    def encode_device(self, texts: Sequence[str], batch_size: int = 64, max_length: int = 512, **_):
+        import torch
+        out = []
+        with torch.no_grad():
+            for i in range(0, len(texts), batch_size):
+                batch = self.tokenizer(list(texts[i:i + batch_size]), padding=True, truncation=True, max_length=max_length,
+                                       return_tensors="pt").to(self.device)
+                cls = self.model(**batch).last_hidden_state[:, 0]
+                out.append(torch.nn.functional.normalize(cls.float(), dim=-1))
+        return torch.cat(out) if out else torch.zeros((0, self.dim), device=self.device)
+
+    def encode_queries_device(self, queries: Sequence[str], **kw):
+        return self.encode_device([self.query_instruction + q for q in queries], **kw)
+
+    def encode(self, texts, **kw) -> np.ndarray:
+        single = isinstance(texts, str)
+        v = self.encode_device([texts] if single else list(texts), **kw).cpu().numpy()
+        return v[0] if single else v
+
+    def encode_queries(self, queries, **kw) -> np.ndarray:
+        single = isinstance(queries, str)
+        v = self.encode_queries_device([queries] if single else list(queries), **kw).cpu().numpy()
+        return v[0] if single else v
+
+
 _dense_encoder_factory: Optional[Callable] = None
 _token_encoder_factory: Optional[Callable] = None
 
@@ -92,11 +140,15 @@ def make_dense_encoder(model_name: str, device):
     try:
         from FlagEmbedding import FlagModel
     except ImportError as e:
+        import os
+        if os.path.isdir(str(model_name)):
+            # a checkpoint directory on disk and no FlagEmbedding: HF transformers on the index's own device
+            return TransformersBgeEncoder(str(model_name), device)
         raise RuntimeError(
-            "no dense encoder: FlagEmbedding is not installed and no encoder was registered "
-            "(legal_rag_b200.retrieval.encoders.register_dense_encoder)") from e
+            "no dense encoder: FlagEmbedding is not installed, the embedding model is not a local checkpoint directory and "
+            "no encoder was registered (legal_rag_b200.retrieval.encoders.register_dense_encoder)") from e
     import torch
-    return FlagModel(model_name, query_instruction_for_retrieval="为这个法律问题生成表示以用于检索相关法律条文：",
+    return FlagModel(model_name, query_instruction_for_retrieval=BGE_QUERY_INSTRUCTION,
                      use_fp16=torch.cuda.is_available(), device=device)      # vector_store.py:70-75
 
 

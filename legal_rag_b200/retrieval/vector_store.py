@@ -147,8 +147,14 @@ class VectorStore:
 
     def search(self, query: str, top_k: int) -> List[Tuple[LawChunk, float]]:
         self.load()
-        q_vec = self._embed([query], is_query=True)
-        scores, idxs = self.index.search(q_vec, top_k)
+        if hasattr(self.model, "encode_queries_device") and self.index.ntotal:
+            # encoder on the index's device: the query vector never visits the host
+            k = min(int(top_k), engine.LRAG_MAX_K)
+            s, i = self.index.search_device(self.model.encode_queries_device([query]), k)
+            scores, idxs = s.cpu().numpy(), i.cpu().numpy()
+        else:
+            q_vec = self._embed([query], is_query=True)
+            scores, idxs = self.index.search(q_vec, top_k)
         hits: List[Tuple[LawChunk, float]] = []
         for score, idx in zip(scores[0], idxs[0]):
             if idx == -1:

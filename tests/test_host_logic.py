@@ -225,3 +225,31 @@ def test_plaid_directory_round_trip(tmp_path):
     with pytest.raises(ValueError, match="embeddings"):
         (tmp_path / "idx" / "doclens.0.json").write_text("[1, 2]")
         plaid.read_plaid_index(tmp_path / "idx")
+
+
+def test_transformers_bge_encoder_matches_flagmodel_semantics(tmp_path):
+    """encoders.TransformersBgeEncoder on a tiny random-init BERT saved to disk (no network): [CLS] pooling, unit norm, the
+    retrieval instruction on queries only -- the behaviour the reference configures FlagModel for (vector_store.py:66-77)."""
+    import torch
+    from transformers import BertConfig, BertModel, BertTokenizerFast
+    vocab = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + list("abcdefghijklmnopqrstuvwxyz") + ["buyer", "seller", "goods", "为", "法", "律"]
+    (tmp_path / "m").mkdir()
+    (tmp_path / "m" / "vocab.txt").write_text("\\n".join(vocab), encoding="utf-8")
+    BertTokenizerFast(vocab_file=str(tmp_path / "m" / "vocab.txt")).save_pretrained(tmp_path / "m")
+    torch.manual_seed(0)
+    BertModel(BertConfig(vocab_size=len(vocab), hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
+                         max_position_embeddings=64)).save_pretrained(tmp_path / "m")
+    enc = encoders.make_dense_encoder(str(tmp_path / "m"), "cpu")
+    assert isinstance(enc, encoders.TransformersBgeEncoder) and enc.dim == 32
+    texts = ["buyer seller goods", "goods"]
+    v = enc.encode(texts)
+    assert v.shape == (2, 32) and v.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-5)
+    tok = enc.tokenizer(texts, padding=True, truncation=True, max_length=512, return_tensors="pt")
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(enc.model(**tok).last_hidden_state[:, 0], dim=-1).numpy()
+    np.testing.assert_allclose(v, ref, atol=1e-6)
+    q = enc.encode_queries(["goods"])
+    np.testing.assert_allclose(q, enc.encode([encoders.BGE_QUERY_INSTRUCTION + "goods"]), atol=1e-6)
+    assert not np.allclose(q[0], v[1], atol=1e-3)                       # the instruction changes the query vector
+    assert enc.encode("goods").shape == (32,)                            # a bare string gives one vector (graph_retriever.py:177)
