@@ -12,6 +12,11 @@ Pinning status ("Oracle"):
   /root/reference/legalrag/retrieval/hybrid_retriever.py:389-551) in this
   container via ``oracle/make_golden.py``; ``oracle/fuse.py`` is checked against
   it in ``tests/test_oracle.py``.
+* graph-expansion scoring -- PINNED: ``tests/golden/graph_golden.json`` was produced by executing the reference's
+  own ``GraphRetriever.search`` (graph_retriever.py:85-219) on fake collaborators; ``oracle/graph.py`` is checked
+  against it.
+* BM25 -- additionally checked against the one known answer rank_bm25 publishes (its README example,
+  ``array([0., 0.93729472, 0.])``), which the transcription reproduces to 5e-9; everything else about it is, like
 * dense / BM25 / MaxSim -- parity unpinned: the arithmetic lives in the
   third-party wheels faiss-cpu 1.13.2, rank-bm25 0.2.2 and colbert-ai 0.2.22,
   none of which is vendored under /root/reference or installed here, and the

@@ -508,3 +508,14 @@ def test_config0_ucc_hybrid_matches_reference_path(eng):
             m = min(len(ref), 120)
             check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
                               100, 2e-3, what=f"config0-{method}")
+
+
+def test_bm25_kernel_reproduces_the_upstream_readme_example(eng):
+    """The rank_bm25 README's published answer (see tests/test_oracle.py) through the CUDA path."""
+    from legal_rag_b200.bm25_index import Bm25HostIndex
+    corpus = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+    host = Bm25HostIndex.from_tokens([d.split(" ") for d in corpus])
+    qi, qt, mx = host.encode_queries(["windy London".split(" ")])
+    s, i = eng.bm25_topk(host.to_device("cuda"), torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), mx, 3)
+    assert i[0].tolist() == [1, 0, 2]
+    np.testing.assert_allclose(s[0].cpu().numpy(), [0.93729472, 0.0, 0.0], rtol=1e-6, atol=1e-7)

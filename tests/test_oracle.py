@@ -170,3 +170,15 @@ def test_graph_scoring_restatement_matches_reference_execution(golden_dir):
             assert a["score"] == pytest.approx(b["score"], rel=1e-6, abs=1e-9) and a["rank"] == b["rank"]
             for key in ("semantic", "depth_decay", "relation_weight", "edge_conf", "graph_depth"):
                 assert a[key] == pytest.approx(b["breakdown"][key], rel=1e-6, abs=1e-9)
+
+
+def test_bm25_oracle_reproduces_the_upstream_readme_example():
+    """rank_bm25's own README (the library the reference calls at bm25_retriever.py:74, pinned >= 0.2.2) documents
+    `bm25.get_scores("windy London".split(" "))` over its three-sentence corpus as array([0., 0.93729472, 0.]) and
+    `get_top_n(..., n=1)` as the London sentence: the one published known answer for this boundary."""
+    corpus = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+    lit = obm25.BM25Okapi([d.split(" ") for d in corpus])
+    scores = lit.get_scores("windy London".split(" "))
+    np.testing.assert_allclose(scores, [0.0, 0.93729472, 0.0], atol=5e-9)
+    s, i = obm25.search(lit, "windy London".split(" "), 1)
+    assert i.tolist() == [1]
