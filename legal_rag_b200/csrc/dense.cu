@@ -410,7 +410,8 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
 // ---------------------------------------------------------------------------------------------
 namespace lrag {
 int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base, const int64_t* col_id,
-                       float* out_score, int64_t* out_id, cudaStream_t stream);
+                       float* out_score, int64_t* out_id, cudaStream_t stream, void* ws = nullptr, size_t ws_bytes = 0);
+size_t topk_select_ws_bytes(int nq, int64_t N, int k);
 
 __global__ void __launch_bounds__(256)
 dense_scores_ref_kernel(const __nv_bfloat16* __restrict__ X, int64_t N, int d, const __nv_bfloat16* __restrict__ Q,

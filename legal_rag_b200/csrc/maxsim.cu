@@ -189,7 +189,8 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 }
 
 int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base, const int64_t* col_id,
-                       float* out_score, int64_t* out_id, cudaStream_t stream);
+                       float* out_score, int64_t* out_id, cudaStream_t stream, void* ws = nullptr, size_t ws_bytes = 0);
+size_t topk_select_ws_bytes(int nq, int64_t N, int k);
 
 static int maxsim_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim, const void* Q, int nq, int Lq,
                          const int64_t* cand, int C, float* out, cudaStream_t stream) {

@@ -247,7 +247,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 }
 
 int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base, const int64_t* col_id,
-                       float* out_score, int64_t* out_id, cudaStream_t stream);
+                       float* out_score, int64_t* out_id, cudaStream_t stream, void* ws = nullptr, size_t ws_bytes = 0);
+size_t topk_select_ws_bytes(int nq, int64_t N, int k);
 
 static size_t scan_qpad_bytes(int nq) { return align_up(size_t((nq + 3) / 4) * SC_BM * SC_DIM * 2, 256); }
 
@@ -302,7 +303,7 @@ using namespace lrag;
 extern "C" size_t lrag_maxsim_scan_workspace_bytes(int64_t Nd, int nq, int k) {
   if (Nd <= 0 || nq <= 0) return 0;
   // padded query block (+ the [nq, Nd] score matrix when the top-k entry point is used: k > 0)
-  return scan_qpad_bytes(nq) + (k > 0 ? align_up(size_t(nq) * size_t(Nd) * 4, 256) : 0);
+  return scan_qpad_bytes(nq) + (k > 0 ? align_up(size_t(nq) * size_t(Nd) * 4, 256) + topk_select_ws_bytes(nq, Nd, k) : 0);
 }
 
 extern "C" int lrag_maxsim_scan_scores_bf16(const void* D, const int32_t* doclen, int64_t Nd, int Ld, int dim, const void* Q,
@@ -324,5 +325,6 @@ extern "C" int lrag_maxsim_scan_topk_bf16(const void* D, const int32_t* doclen, 
   float* S = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + scan_qpad_bytes(nq));
   int rc = scan_launch(D, doclen, Nd, Ld, dim, Q, nq, Lq, S, Nd, ws, stream);
   if (rc) return rc;
-  return launch_topk_select(S, Nd, nq, Nd, k, id_base, nullptr, out_score, out_id, stream);
+  uint8_t* sel_ws = reinterpret_cast<uint8_t*>(S) + align_up(size_t(nq) * size_t(Nd) * 4, 256);
+  return launch_topk_select(S, Nd, nq, Nd, k, id_base, nullptr, out_score, out_id, stream, sel_ws, topk_select_ws_bytes(nq, Nd, k));
 }

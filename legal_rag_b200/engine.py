@@ -99,7 +99,9 @@ def topk_select(S: torch.Tensor, k: int, id_base: int = 0, col_id: Optional[torc
     if col_id is not None:
         col_id = _need(col_id, torch.int64, 2, "col_id")
     s, i = _out(nq, k, S.device)
-    check(lib.lrag_topk_select_f32(_ptr(S), N, nq, N, k, id_base, _ptr(col_id), _ptr(s), _ptr(i), None, 0, _stream()),
+    nbytes = lib.lrag_topk_select_workspace_bytes(nq, N, k)       # long rows are selected slice by slice
+    ws = _ws(nbytes, S.device) if nbytes else None
+    check(lib.lrag_topk_select_f32(_ptr(S), N, nq, N, k, id_base, _ptr(col_id), _ptr(s), _ptr(i), _ptr(ws), nbytes, _stream()),
           "lrag_topk_select_f32")
     return s, i
 

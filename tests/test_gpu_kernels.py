@@ -43,7 +43,8 @@ def _bf16(x):
 # ---------------------------------------------------------------- select / merge
 def test_topk_select_matches_oracle(eng):
     rng = np.random.default_rng(0)
-    for nq, N, k in [(3, 1000, 100), (5, 37, 64), (2, 70000, 1024), (4, 100, 100), (1, 1, 1)]:
+    # rows longer than 2^18 scores take the sliced single-pass path (slices + merge)
+    for nq, N, k in [(3, 1000, 100), (5, 37, 64), (2, 70000, 1024), (4, 100, 100), (1, 1, 1), (3, 700_001, 100), (2, 1_100_000, 1024)]:
         S = rng.standard_normal((nq, N)).astype(np.float32)
         S[:, ::7] = S[:, :1]                      # plenty of exact ties -> lower id first
         s, i = eng.topk_select(torch.from_numpy(S).cuda(), k, id_base=1000)
@@ -54,17 +55,17 @@ def test_topk_select_matches_oracle(eng):
 
 def test_topk_select_with_col_ids_and_skips(eng):
     rng = np.random.default_rng(1)
-    nq, C, k = 4, 300, 50
-    S = rng.standard_normal((nq, C)).astype(np.float32)
-    ids = np.stack([rng.permutation(10000)[:C] for _ in range(nq)]).astype(np.int64)
-    ids[:, 5::11] = -1
-    S[0, :40] = 0.25                              # ties resolved by id, not by column
-    s, i = eng.topk_select(torch.from_numpy(S).cuda(), k, col_id=torch.from_numpy(ids).cuda())
-    for q in range(nq):
-        ok = np.nonzero(ids[q] >= 0)[0]
-        order = ok[np.lexsort((ids[q, ok], -S[q, ok].astype(np.float64)))][:k]
-        np.testing.assert_array_equal(i[q].cpu().numpy(), ids[q, order])
-        np.testing.assert_array_equal(s[q].cpu().numpy(), S[q, order])
+    for nq, C, k, pool in [(4, 300, 50, 10000), (2, 600_000, 100, 5_000_000)]:      # the second shape is sliced
+        S = rng.standard_normal((nq, C)).astype(np.float32)
+        ids = np.stack([rng.permutation(pool)[:C] for _ in range(nq)]).astype(np.int64)
+        ids[:, 5::11] = -1
+        S[0, :40] = 9.25                          # ties resolved by id, not by column
+        s, i = eng.topk_select(torch.from_numpy(S).cuda(), k, col_id=torch.from_numpy(ids).cuda())
+        for q in range(nq):
+            ok = np.nonzero(ids[q] >= 0)[0]
+            order = ok[np.lexsort((ids[q, ok], -S[q, ok].astype(np.float64)))][:k]
+            np.testing.assert_array_equal(i[q].cpu().numpy(), ids[q, order])
+            np.testing.assert_array_equal(s[q].cpu().numpy(), S[q, order])
 
 
 def test_topk_merge_matches_oracle(eng):
