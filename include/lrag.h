@@ -112,7 +112,7 @@ int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q
  * BM25 channel.  Replaces `bm25.get_scores(tokens)` + the full Python sort at
  * legalrag/retrieval/bm25_retriever.py:74-75 (rank_bm25.BM25Okapi).
  * Index = term-major CSR with doc ids ascending inside each term:
- *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard, 16-byte aligned), impact [nnz] fp32
+ *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard), impact [nnz] fp32, both 16-byte aligned
  *   = idf[t] * tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))  with GLOBAL idf/avgdl.
  * Queries = CSR of term ids: q_indptr [nq+1] int64, q_term [*] int32 (repeats allowed and
  * scored once per occurrence, -1 / out-of-range = OOV).
@@ -129,7 +129,7 @@ int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q
  * reproducible; a bound that is too small lets a score overflow. */
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
 /* Tuning knob (process-wide; call before sizing the workspace): documents per work item =
- * slabs * 16384.  Small items keep the posting ranges all queries are working on inside L2;
+ * slabs * 12288.  Small items keep the posting ranges all queries are working on inside L2;
  * large items amortise the per-item state hand-off.  0 restores the default (32, or the
  * LRAG_BM25_ITEM_SLABS environment variable). */
 int lrag_bm25_set_item_slabs(int slabs);
