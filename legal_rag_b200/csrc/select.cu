@@ -121,8 +121,14 @@ topk_slice_kernel(const float* __restrict__ S, int64_t ld, int64_t N, int k, int
     int64_t c0[SELECT_UNROLL / 4];
 #pragma unroll
     for (int g = 0; g < SELECT_UNROLL / 4; ++g) c0[g] = base + (int64_t(g) * SELECT_THREADS + tid) * 4;
+    // common case once the threshold has settled: nothing in this warp's 512 scores reaches it (one max tree, one vote)
+    float vmax = v[0];
+#pragma unroll
+    for (int u = 1; u < SELECT_UNROLL; ++u) vmax = fmaxf(vmax, v[u]);
+    const bool warp_hit = __any_sync(0xffffffffu, vmax >= thr_s);
 #pragma unroll
     for (int u = 0; u < SELECT_UNROLL; ++u) {
+      if (!warp_hit) break;
       const int64_t c = VEC ? c0[u / 4] + (u & 3) : base + tid + int64_t(u) * SELECT_THREADS;
       bool want = c < hi && v[u] >= thr_s;
       if (__any_sync(0xffffffffu, want)) {
