@@ -20,3 +20,6 @@ echo "exit $? : $(tail -1 gpurun_out/test_retrievers.log)" | tee -a gpurun_out/t
 echo "=== fullsize" | tee -a gpurun_out/tests.log
 timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/test_fullsize.log 2>&1
 echo "exit $? : $(tail -1 gpurun_out/test_fullsize.log)" | tee -a gpurun_out/tests.log
+echo "=== fuzz" | tee -a gpurun_out/tests.log
+timeout 900 python -m pytest tests/test_gpu_fuzz.py -m gpu -x -q > gpurun_out/test_fuzz.log 2>&1
+echo "exit $? : $(tail -1 gpurun_out/test_fuzz.log)" | tee -a gpurun_out/tests.log
