@@ -334,7 +334,7 @@ class HybridWorkload:
 
     def __init__(self, args, rank, world, device):
         self.N, self.d, self.V = args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
-        self.nq, self.k, self.kc = args.nq or 4096, args.k, args.k
+        self.nq, self.k, self.kc = args.nq or 4096, args.k, (getattr(args, "kc", 0) or args.k)
         self.colbert_mode = getattr(args, "colbert_mode", "rerank")
         # rerank: configs[4]'s 1M-doc token store (ids aliased onto it); scan: one token row per document of the shard
         self.Nd_tok, self.Ld, self.Lq = (max(1, self.N // 100), 128, 32) if self.colbert_mode == "rerank" else (self.N, 128, 32)
@@ -666,6 +666,7 @@ def main():
     ap.add_argument("--nq", type=int, default=0)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--mean-len", type=float, default=0.0, help="bm25: mean document length of the synthetic corpus (default 40)")
+    ap.add_argument("--kc", type=int, default=0, help="hybrid: per-channel list length (default k); 500 gives the 1000-candidate rerank of SURVEY 8d C5")
     ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
                     help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
