@@ -8,7 +8,9 @@
 One "step" = one pass of the hot path over one batch of synthetic queries.  At N=1 the default
 workload is BASELINE.json configs[1] (dense flat-IP top-100, 10M x 1024 bf16, 4096 queries).  With N
 ranks every rank owns its own 10M-row shard (the corpus grows to N x 10M: weak scaling), computes its
-local top-k and the lists are merged after one NCCL all-gather.
+local top-k and the lists are merged after one NCCL all-gather.  The default run then adds a "hybrid" object to
+the same line: every rank's 1/8 shard of configs[4] (12.5M x 768 dense rows + BM25 + ColBERT rerank + fusion)
+through the sharded hybrid pipeline, measured the same way (--no-hybrid-block skips it).
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -653,6 +655,84 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+def release(wl):
+    """Drops a workload's device stores (the CPU leg only needs its shape attributes)."""
+    import gc
+    import torch
+    for name, v in list(vars(wl).items()):
+        if not isinstance(v, (int, float, str, bool, dict, type(None), torch.device)) and name not in ("torch", "engine"):
+            delattr(wl, name)
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks):
+    """Sets a workload up, times `steps` steps after `warmup` (barrier + synchronize on both sides, CUDA events, max over ranks),
+    then the same through the host-buffer API.  Returns the JSON line's fields on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from legal_rag_b200 import engine
+    wl.setup()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        wl.step()
+    barrier()
+    engine.prof_enable(steps * 16 + 8)
+    launches0 = engine.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        wl.step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    launches = engine.launch_count() - launches0
+    prof = engine.prof_collect()
+    engine.prof_enable(0)
+    kern = [t for name, t in prof if name == wl.dominant]
+    kernel_ms = sum(kern) / steps        # per step (a step may launch the dominant kernel several times)
+
+    # ---- end to end through the host-buffer API: H2D queries -> search -> D2H results, every step ----
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        wl.e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, kernel_ms = t.tolist()
+    if rank != 0:
+        return None
+    units = wl.units_per_step() * steps
+    h2d, d2h = wl.e2e_bytes()
+    return {"metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
+            "data": "synthetic (seeded, generated on device; random unit-norm vectors)", "config": wl.config(),
+            "clocks": clocks,
+            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / steps},
+            "gpu_launches": launches,
+            "roofline": wl.roofline(kernel_ms, peaks),
+            "global_queries_per_s": wl.nq * steps / (ms * 1e-3)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -670,6 +750,8 @@ def main():
     ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
                     help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hybrid-block", action="store_true",
+                    help="default workload only: skip the extra 'hybrid' object (every rank's shard of configs[4] through the hybrid pipeline)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -691,68 +773,25 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from legal_rag_b200 import engine
 
-    wl = WORKLOADS[args.workload](args, rank, world, device)
-    wl.setup()
     peaks = measured_peaks()
+    wl = WORKLOADS[args.workload](args, rank, world, device)
+    line = measure_native(wl, args.steps, args.warmup, rank, world, local_rank, device, peaks)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        wl.step()
-    barrier()
-    engine.prof_enable(args.steps * 16 + 8)
-    launches0 = engine.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        out = wl.step()
-    ev1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    launches = engine.launch_count() - launches0
-    prof = engine.prof_collect()
-    engine.prof_enable(0)
-    kern = [t for name, t in prof if name == wl.dominant]
-    kernel_ms = sum(kern) / args.steps        # per step (a step may launch the dominant kernel several times)
-
-    # ---- end to end through the host-buffer API: H2D queries -> search -> D2H results, every step ----
-    for _ in range(2):
-        wl.e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        wl.e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
-
-    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = t.tolist()
+    # The metric's own multi-GPU configuration next to the configs[1] line: every rank's 1/8 shard of configs[4] through the
+    # sharded hybrid pipeline (a shorter timed region; same rules).  8 ranks hold exactly configs[4].
+    if args.workload == "dense" and not args.no_hybrid_block and not (args.n_docs or args.dim or args.nq):
+        wl_h = WORKLOADS["hybrid"](args, rank, world, device)
+        release(wl)
+        try:
+            h = measure_native(wl_h, max(1, min(args.steps, 5)), args.warmup, rank, world, local_rank, device, peaks)
+        except Exception as exc:       # the configs[1] line above stands on its own
+            h = {"error": f"{type(exc).__name__}: {exc}"}
+        release(wl_h)
+        if rank == 0:
+            line["hybrid"] = h if "error" in h else {key: h[key] for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config",
+                                                      "clocks", "e2e", "gpu_launches", "roofline", "global_queries_per_s")}
 
     if rank == 0:
-        units = wl.units_per_step() * args.steps
-        value = units / (ms * 1e-3)
-        h2d, d2h = wl.e2e_bytes()
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
-                "data": "synthetic (seeded, generated on device; random unit-norm vectors)", "config": wl.config(),
-                "clocks": clocks,
-                "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches,
-                "roofline": wl.roofline(kernel_ms, peaks),
-                "global_queries_per_s": wl.nq * args.steps / (ms * 1e-3)}
         if not args.no_cpu_baseline:
             run, sample = wl.cpu_sample()
             run()

@@ -128,13 +128,6 @@ __device__ __forceinline__ int lower_bound_doc(const int32_t* __restrict__ ids, 
   return lo;
 }
 
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 // 4-byte asynchronous global -> shared copy of the executing thread, and the arrive that fires on an
 // mbarrier once all of this thread's earlier copies have landed (pending count +1 now, -1 then)
 __device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {

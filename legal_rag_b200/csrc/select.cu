@@ -5,6 +5,7 @@
 //                            of MaxSim candidate scores (colbert_retriever.py:152, Searcher.search)
 //   lrag_topk_merge       <- no reference counterpart (the reference is single-process)
 #include "select.cuh"
+#include <algorithm>
 
 namespace lrag {
 
@@ -55,134 +56,304 @@ topk_merge_kernel(const float* score, const int64_t* id, int L, int k, int P, fl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Long rows: one CTA per row would read the row once per radix pass from a single SM.  Instead the row is cut into
-// slices; a slice CTA streams its scores ONCE (coalesced), keeps only those that beat its running threshold in a
-// shared-memory candidate buffer (an exact radix select cuts the buffer back to k and raises the threshold whenever it
-// fills), and writes its k best keys; a second kernel merges the slices' lists.  HBM traffic = the row, once.
+// Long rows (or many medium rows): one CTA per row would read the row once per radix pass from a single SM.  Instead a
+// CTA streams a part of a row ONCE, keeps only the scores that beat its running threshold in a shared-memory candidate
+// buffer (an exact radix select cuts the buffer back to k and raises the threshold whenever it fills), and writes its k
+// best keys; a second kernel merges the lists of a row.  HBM traffic = the matrix, once.
+//
+// topk_stream_kernel (16-byte aligned rows).  The matrix is cut into trips of 4096 scores, numbered row-major, and every
+// CTA of a one-wave grid (2 per SM) takes an equal, contiguous run of trips: no wave tail, and a run that covers
+// hundreds of thousands of scores of a row has a threshold that only ~k ln(n) scores ever beat.  A run may cross row ends; the
+// CTA then emits its list for the finished row and starts over.  Trips arrive through a shared-memory ring of 16 KB
+// stages filled by bulk asynchronous copies (cp.async.bulk, completion on mbarriers) that thread 0 keeps three trips
+// ahead of the filter, so the bytes in flight per SM do not depend on how the filter's barriers fall.  The filter is per
+// thread: a thread whose 16 scores stay below the threshold does nothing.  The first trip of a row sets a threshold
+// without a select: the k-th largest of the 256 per-thread maxima of the trip has k scores at or above it.
+// topk_slice_kernel: the same filter over plain loads and fixed slices, for rows that are not 16-byte aligned.
 // ------------------------------------------------------------------------------------------------
 constexpr int64_t SELECT_SLICE = int64_t(1) << 18;      // scores per slice CTA (1 MB)
-constexpr int SELECT_UNROLL = 16;                        // scores per thread per trip (four 16-byte loads when rows are aligned)
+constexpr int STREAM_THREADS = 512;                      // topk_stream_kernel: 16 warps, two CTAs per SM
+constexpr int STREAM_PER_THREAD = 8;                     // scores per thread per trip (two 16-byte shared-memory loads)
+constexpr int STREAM_TRIP = STREAM_THREADS * STREAM_PER_THREAD;      // 4096 scores = one 16 KB ring stage
+constexpr int STREAM_STAGES = 4;
+constexpr int SELECT_UNROLL = 16;                        // topk_slice_kernel: scores per thread per trip
 constexpr int SELECT_TRIP = SELECT_THREADS * SELECT_UNROLL;
-constexpr int SELECT_CAP = LRAG_MAX_K + SELECT_TRIP;     // candidate keys: at most k survivors + one trip
+static_assert(SELECT_TRIP == STREAM_TRIP, "both kernels size the candidate buffer for the same trip");
+constexpr int SELECT_CAP = LRAG_MAX_K + SELECT_TRIP;     // topk_slice_kernel's candidate keys: at most LRAG_MAX_K kept + one trip
 
 struct SliceCands {
   const uint64_t* c; int n;
   template <class F> __device__ void operator()(F&& f) const {
-    for (int i = threadIdx.x; i < n; i += SELECT_THREADS) f(c[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint64_t key = c[i]; if (key) f(key); }
   }
 };
 
-template <bool VEC>
+// State of a streaming CTA's filter: candidate buffer [trig + one trip], survivor buffer [P], running threshold (as a key
+// and as a score).  `trig` = candidate count above which the buffer is cut back to its k best after a trip: a few times k,
+// so that the threshold follows the scores seen so far closely (a compaction costs a few hundred instructions per warp,
+// an insert ~15, and inserts fall as k / scores seen only while the threshold keeps up).
+struct SliceFilter {
+  uint64_t* cand; uint64_t* keep; SelectShared* ss; int* cnt; int* cnt2; int trig;
+  unsigned long long thr_key; float thr_s;
+  bool over = false;      // one of this thread's inserts of the current trip landed at or past `trig`
+
+  // one score that reached the threshold: make its key, append it.  `col` = its column in the row, `cid` = the row's
+  // column ids (or null; a negative id marks a column that does not take part)
+  __device__ __forceinline__ void offer(float s, uint32_t col, const int64_t* cid) {
+    uint32_t tie = col;
+    bool ok = true;
+    if (cid) { const int64_t id = cid[col]; ok = id >= 0; tie = uint32_t(id); }
+    const uint64_t key = make_key(s, tie);
+    if (ok && key > thr_key) {
+      // one plain shared-memory atomic per hit: hits are rare and scattered over the warp, so the vote / popc / shuffle
+      // sequence of a warp-aggregated increment (what atomicAdd compiles to) costs more than it saves
+      uint32_t at;
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(smem_u32(cnt)) : "memory");
+      cand[at] = key;                                        // never past trig + one trip: see trip_barrier()
+      over |= int(at) >= trig;
+    }
+  }
+  // Score at or below every key >= pivot.  A pivot that the select left as a bin prefix (low bits zero) can decode to a
+  // NaN when the k-th score is -inf; nothing compares >= NaN, so that case falls back to "no threshold".
+  static __device__ __forceinline__ float floor_score(unsigned long long pivot) {
+    const float s = key_score(pivot);
+    return s == s ? s : -INFINITY;
+  }
+  // start of a new row (every thread, behind a __syncthreads)
+  __device__ __forceinline__ void reset() {
+    if (threadIdx.x == 0) *cnt = 0;
+    thr_key = 0ull; thr_s = -INFINITY;
+    __syncthreads();
+  }
+  // End of a trip, every thread: the CTA barrier, which also tells whether more than `trig` candidates are held now.  The
+  // verdict travels with the barrier (some thread's insert index reached trig) instead of being read from `cnt`
+  // afterwards: a warp that runs ahead into the next trip may already be inserting while a slower warp still decides.
+  __device__ __forceinline__ bool trip_barrier() {
+    const bool need = __syncthreads_or(over);
+    over = false;
+    return need;
+  }
+  // keep the k best (every thread, when trip_barrier() said so)
+  __device__ __forceinline__ void compact(int k) {
+    const int tid = threadIdx.x, n = *cnt;
+    SliceCands cs{cand, n};
+    const unsigned long long pivot = block_select_pivot(cs, k, *ss);
+    if (tid == 0) *cnt2 = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint64_t key = cand[i];
+      if (key && key >= pivot) keep[atomicAdd(cnt2, 1)] = key;
+    }
+    __syncthreads();
+    const int m = *cnt2;
+    for (int i = tid; i < m; i += blockDim.x) cand[i] = keep[i];
+    if (tid == 0) *cnt = m;
+    if (pivot > thr_key) { thr_key = pivot; thr_s = floor_score(pivot); }
+    __syncthreads();
+  }
+  // the k best held (unsorted; 0 = empty)
+  __device__ __forceinline__ void emit(int k, uint64_t* out) {
+    const int tid = threadIdx.x, n = *cnt;
+    SliceCands cs{cand, n};
+    const unsigned long long pivot = block_select_pivot(cs, k, *ss);
+    if (tid == 0) *cnt2 = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint64_t key = cand[i];
+      if (key && key >= pivot) { const int at = atomicAdd(cnt2, 1); if (at < k) out[at] = key; }
+    }
+    __syncthreads();
+    for (int i = *cnt2 + tid; i < k; i += blockDim.x) out[i] = 0;
+    __syncthreads();
+  }
+};
+
+// Balanced cut of an [nq, N] matrix into runs of trips, one run per CTA (see topk_stream_kernel).
+struct StreamPlan {
+  int tpr;         // trips per row
+  int units;       // nq * tpr
+  int grid;        // CTAs
+  int seg_trips;   // trips per CTA (the last CTA may have fewer)
+  int spr;         // list slots per row: a row is covered by at most this many CTAs
+  int trig;        // candidate count that triggers a compaction (the candidate buffer holds trig + one trip)
+};
+
+struct OneKey {
+  uint64_t key;
+  template <class F> __device__ void operator()(F&& f) const { f(key); }
+};
+
+// 32-bit shared-window addressing for the per-trip instructions (no generic -> shared conversions in the loop)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 x;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(addr));
+  return x;
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    if (ok) return;
+    if (t0 == 0) t0 = clock64();
+    else if (clock64() - t0 > 20000000000LL) { printf("lrag: select ring wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS)
+topk_stream_kernel(const float* __restrict__ S, int64_t ld, int64_t N, int k, const int64_t* __restrict__ col_id, StreamPlan plan,
+                   uint64_t* __restrict__ out_keys) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  float* ring = reinterpret_cast<float*>(sm_raw);                                     // [STREAM_STAGES][STREAM_TRIP]
+  uint64_t* cand = reinterpret_cast<uint64_t*>(ring + STREAM_STAGES * STREAM_TRIP);   // [trig + STREAM_TRIP], then [P] survivors
+  __shared__ SelectShared ss;
+  __shared__ int cnt, cnt2;
+  __shared__ __align__(8) uint64_t full[STREAM_STAGES];
+  const int tid = threadIdx.x;
+  const int u0 = blockIdx.x * plan.seg_trips;                                         // this CTA's run of trips [u0, u1)
+  const int u1 = min(plan.units, u0 + plan.seg_trips);
+  const int tpr = plan.tpr;
+  const int n_last = int(N - int64_t(tpr - 1) * STREAM_TRIP);                         // scores in a row's last trip
+  const bool boot_ok = k <= STREAM_THREADS && !col_id;
+  SliceFilter f{cand, cand + plan.trig + STREAM_TRIP, &ss, &cnt, &cnt2, plan.trig, 0ull, -INFINITY};
+
+  // Producer side (thread 0): trip (iq, itr) -> the next ring stage.  Whole 16-byte groups come by bulk copy; the <= 3
+  // scores behind the last whole group of a row are read directly by the filter.
+  int iq = u0 / tpr, itr = u0 - iq * tpr, istage = 0, iu = u0;
+  auto issue = [&]() {
+    const int n = itr == tpr - 1 ? n_last : STREAM_TRIP;
+    const uint32_t bytes = uint32_t(n & ~3) * 4u;
+    if (bytes) {
+      mbar_arrive_expect_tx(&full[istage], bytes);
+      bulk_copy_g2s(ring + istage * STREAM_TRIP, S + size_t(iq) * ld + size_t(itr) * STREAM_TRIP, bytes, &full[istage]);
+    } else {
+      mbar_arrive(&full[istage]);
+    }
+    if (++itr == tpr) { itr = 0; ++iq; }
+    if (++istage == STREAM_STAGES) istage = 0;
+    ++iu;
+  };
+  if (tid == 0) {
+    for (int s = 0; s < STREAM_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+    cnt = 0;
+  }
+  __syncthreads();
+  if (tid == 0)
+    while (iu < u1 && iu < u0 + STREAM_STAGES) issue();
+
+  // Consumer side.  A thread's 8 scores of a trip: groups g = 0, 1 of four consecutive scores at trip offset (g * 512 + tid) * 4.
+  const uint32_t ring_s = smem_u32(ring) + uint32_t(tid) * 16u, full_s = smem_u32(full);
+  uint32_t stage = 0, parity = 0;
+  int q = u0 / tpr, tr = u0 - q * tpr;
+  for (int u = u0; u < u1;) {
+    // the part of row q inside this run: trips [tr, tr_end)
+    const int tr_end = min(tpr, tr + (u1 - u));
+    const float* row = S + size_t(q) * ld;
+    const int64_t* cid = col_id ? col_id + size_t(q) * N : nullptr;
+    bool row_start = true;
+    for (; tr < tr_end; ++tr, ++u) {
+      float v[STREAM_PER_THREAD];
+      mbar_wait_s(full_s + stage * 8u, parity);
+      const uint32_t st = ring_s + stage * uint32_t(STREAM_TRIP * 4);
+      if (tr != tpr - 1 || n_last == STREAM_TRIP) {
+#pragma unroll
+        for (int g = 0; g < STREAM_PER_THREAD / 4; ++g) {
+          const float4 x = lds128(st + g * STREAM_THREADS * 16);
+          v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+        }
+      } else {
+        const int whole = n_last & ~3;
+        const float qnan = __int_as_float(0x7fc00000);      // past the row's end: NaN never reaches a threshold
+#pragma unroll
+        for (int g = 0; g < STREAM_PER_THREAD / 4; ++g) {
+          const int e = (g * STREAM_THREADS + tid) * 4;
+          float4 x = make_float4(qnan, qnan, qnan, qnan);
+          if (e + 3 < whole) x = lds128(st + g * STREAM_THREADS * 16);
+          else if (e < n_last) {     // ragged end of the row: its last (partial) group comes straight from global memory
+            const float* tail = row + size_t(tr) * STREAM_TRIP + e;
+            x.x = __ldg(tail);
+            if (e + 1 < n_last) x.y = __ldg(tail + 1);
+            if (e + 2 < n_last) x.z = __ldg(tail + 2);
+          }
+          v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+        }
+      }
+      float vmax = v[0];
+#pragma unroll
+      for (int i = 1; i < STREAM_PER_THREAD; ++i) vmax = fmaxf(vmax, v[i]);
+      if (row_start && boot_ok) {
+        // a threshold without streaming anything twice: the k-th largest of the 512 per-thread maxima of the row's first
+        // trip has k scores of the row at or above it (a thread with no score inside the row counts as -inf)
+        const OneKey mine{make_key(vmax == vmax ? vmax : -INFINITY, uint32_t(tid))};
+        f.thr_s = SliceFilter::floor_score(block_select_pivot(mine, k, ss));
+      }
+      row_start = false;
+      if (vmax >= f.thr_s) {
+        const uint32_t col0 = uint32_t(tr) * STREAM_TRIP + uint32_t(tid) * 4u;
+#pragma unroll
+        for (int i = 0; i < STREAM_PER_THREAD; ++i)
+          if (v[i] >= f.thr_s) f.offer(v[i], col0 + (i / 4) * STREAM_THREADS * 4 + (i & 3), cid);
+      }
+      const bool full_buf = f.trip_barrier();    // every thread holds its scores in registers: the stage is free
+      if (tid == 0 && iu < u1) issue();
+      if (full_buf) f.compact(k);
+      if (++stage == STREAM_STAGES) { stage = 0; parity ^= 1; }
+    }
+    // end of the row or of the run: this CTA's list for row q goes to slot (CTA - first CTA that holds trips of q)
+    f.emit(k, out_keys + (size_t(q) * plan.spr + (blockIdx.x - (q * tpr) / plan.seg_trips)) * k);
+    f.reset();
+    tr = 0; ++q;
+  }
+}
+
 __global__ void __launch_bounds__(SELECT_THREADS)
 topk_slice_kernel(const float* __restrict__ S, int64_t ld, int64_t N, int k, int P, const int64_t* __restrict__ col_id, int64_t slice_len,
                   int nslices, uint64_t* __restrict__ out_keys) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  uint64_t* cand = reinterpret_cast<uint64_t*>(sm_raw);           // [SELECT_CAP]
-  uint64_t* keep = cand + SELECT_CAP;                              // [P] survivors of a compaction
+  uint64_t* cand = reinterpret_cast<uint64_t*>(sm_raw);           // [SELECT_CAP], then [P] survivors of a compaction
   __shared__ SelectShared ss;
   __shared__ int cnt, cnt2;
-  const int q = blockIdx.y, sl = blockIdx.x;
+  const int q = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
   const int64_t lo = int64_t(sl) * slice_len;
-  const int64_t hi = lo + slice_len < N ? lo + slice_len : N;
-  const float* row = S + size_t(q) * ld;
+  const int n_slice = int((lo + slice_len < N ? lo + slice_len : N) - lo);
+  const float* src = S + size_t(q) * ld + lo;
   const int64_t* cid = col_id ? col_id + size_t(q) * N : nullptr;
-  const int tid = threadIdx.x, lane = tid & 31;
-  unsigned long long thr_key = 0ull;
-  float thr_s = -INFINITY;
+  const uint32_t tie0 = uint32_t(lo);
+  SliceFilter f{cand, cand + SELECT_CAP, &ss, &cnt, &cnt2, SELECT_CAP - SELECT_TRIP, 0ull, -INFINITY};
   if (tid == 0) cnt = 0;
   __syncthreads();
   // one trip of scores per thread; the next trip's loads are issued before this one is filtered
-  auto load_trip = [&](int64_t base, float (&v)[SELECT_UNROLL]) {
-    if (VEC) {
+  auto load_trip = [&](int base, float (&v)[SELECT_UNROLL]) {
 #pragma unroll
-      for (int g = 0; g < SELECT_UNROLL / 4; ++g) {
-        const int64_t c = base + (int64_t(g) * SELECT_THREADS + tid) * 4;
-        float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (c + 3 < hi) x = __ldg(reinterpret_cast<const float4*>(row + c));
-        else {
-          if (c < hi) x.x = __ldg(row + c);
-          if (c + 1 < hi) x.y = __ldg(row + c + 1);
-          if (c + 2 < hi) x.z = __ldg(row + c + 2);
-        }
-        v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < SELECT_UNROLL; ++u) {
-        const int64_t c = base + tid + int64_t(u) * SELECT_THREADS;
-        v[u] = c < hi ? __ldg(row + c) : -INFINITY;
-      }
+    for (int u = 0; u < SELECT_UNROLL; ++u) {
+      const int off = base + tid + u * SELECT_THREADS;
+      v[u] = off < n_slice ? __ldg(src + off) : -INFINITY;
     }
   };
   float v[SELECT_UNROLL], vn[SELECT_UNROLL];
-  load_trip(lo, v);
-  for (int64_t base = lo; base < hi; base += SELECT_TRIP) {
-    if (base + SELECT_TRIP < hi) load_trip(base + SELECT_TRIP, vn);
-    int64_t c0[SELECT_UNROLL / 4];
-#pragma unroll
-    for (int g = 0; g < SELECT_UNROLL / 4; ++g) c0[g] = base + (int64_t(g) * SELECT_THREADS + tid) * 4;
-    // common case once the threshold has settled: nothing in this warp's 512 scores reaches it (one max tree, one vote)
+  load_trip(0, v);
+  for (int base = 0; base < n_slice; base += SELECT_TRIP) {
+    if (base + SELECT_TRIP < n_slice) load_trip(base + SELECT_TRIP, vn);
     float vmax = v[0];
 #pragma unroll
     for (int u = 1; u < SELECT_UNROLL; ++u) vmax = fmaxf(vmax, v[u]);
-    const bool warp_hit = __any_sync(0xffffffffu, vmax >= thr_s);
+    if (vmax >= f.thr_s) {
 #pragma unroll
-    for (int u = 0; u < SELECT_UNROLL; ++u) {
-      if (!warp_hit) break;
-      const int64_t c = VEC ? c0[u / 4] + (u & 3) : base + tid + int64_t(u) * SELECT_THREADS;
-      bool want = c < hi && v[u] >= thr_s;
-      if (__any_sync(0xffffffffu, want)) {
-        uint64_t key = 0;
-        if (want) {
-          uint32_t tie = uint32_t(c);
-          if (cid) { const int64_t id = cid[c]; want = id >= 0; tie = uint32_t(id); }
-          key = make_key(v[u], tie);
-          want = want && key > thr_key;
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, want);
-        if (m) {
-          int at = 0;
-          if (lane == __ffs(m) - 1) at = atomicAdd(&cnt, __popc(m));
-          at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
-          if (want) cand[at + __popc(m & ((1u << lane) - 1))] = key;       // never past SELECT_CAP: see the trigger below
-        }
+      for (int u = 0; u < SELECT_UNROLL; ++u) {
+        const int off = base + tid + u * SELECT_THREADS;
+        if (v[u] >= f.thr_s && off < n_slice) f.offer(v[u], tie0 + uint32_t(off), cid);
       }
     }
-    __syncthreads();
-    if (cnt > SELECT_CAP - SELECT_TRIP) {
-      // the next trip could overflow: keep the k best, their worst becomes the threshold
-      const int n = cnt;
-      SliceCands cs{cand, n};
-      const unsigned long long pivot = block_select_pivot(cs, k, ss);
-      if (tid == 0) cnt2 = 0;
-      __syncthreads();
-      for (int i = tid; i < n; i += SELECT_THREADS) {
-        const uint64_t key = cand[i];
-        if (key >= pivot) keep[atomicAdd(&cnt2, 1)] = key;
-      }
-      __syncthreads();
-      const int m = cnt2;
-      for (int i = tid; i < m; i += SELECT_THREADS) cand[i] = keep[i];
-      if (tid == 0) cnt = m;
-      if (pivot > thr_key) { thr_key = pivot; thr_s = key_score(pivot); }
-      __syncthreads();
-    }
+    if (f.trip_barrier()) f.compact(k);
 #pragma unroll
     for (int u = 0; u < SELECT_UNROLL; ++u) v[u] = vn[u];
   }
-  // this slice's k best (unsorted; 0 = empty)
-  const int n = cnt;
-  SliceCands cs{cand, n};
-  const unsigned long long pivot = block_select_pivot(cs, k, ss);
-  uint64_t* out = out_keys + (size_t(q) * nslices + sl) * k;
-  if (tid == 0) cnt2 = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += SELECT_THREADS) {
-    const uint64_t key = cand[i];
-    if (key >= pivot) { const int at = atomicAdd(&cnt2, 1); if (at < k) out[at] = key; }
-  }
-  __syncthreads();
-  for (int i = cnt2 + tid; i < k; i += SELECT_THREADS) out[i] = 0;
+  f.emit(k, out_keys + (size_t(q) * nslices + sl) * k);
 }
 
 struct KeyList {
@@ -193,52 +364,93 @@ struct KeyList {
 };
 
 __global__ void __launch_bounds__(SELECT_THREADS)
-topk_merge_keys_kernel(const uint64_t* keys, int L, int k, int P, int64_t id_base, float* out_score, int64_t* out_id) {
+topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id_base, float* out_score, int64_t* out_id, StreamPlan plan) {
   extern __shared__ uint8_t sm_raw[];
   __shared__ SelectShared ss;
   const int q = blockIdx.x;
-  KeyList lists{keys + size_t(q) * L, L};
-  block_topk_sorted(lists, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), id_base, out_score + size_t(q) * k,
+  int lists = slots;                           // fixed slices: every slot of the row was written
+  if (plan.seg_trips > 0)                      // balanced runs: the CTAs that hold trips of row q wrote the first `lists` slots
+    lists = ((q + 1) * plan.tpr - 1) / plan.seg_trips - (q * plan.tpr) / plan.seg_trips + 1;
+  KeyList rows{keys + size_t(q) * slots * k, lists * k};
+  block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), id_base, out_score + size_t(q) * k,
                     out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr));
 }
 
-// Slice length for a problem: 2^18 scores when that already gives every SM several CTAs, shorter (down to 2^15, a multiple
-// of the trip) when there are few rows.
+// Slice length of the fixed-slice path: 2^18 scores when that already gives every SM several CTAs, shorter (down to 2^15, a
+// multiple of the trip) when there are few rows.
 static int64_t select_slice_len(int nq, int64_t N) {
   const int64_t want_ctas = 8 * int64_t(sm_count());
   int64_t len = SELECT_SLICE;
   while (len > (int64_t(1) << 15) && int64_t(nq) * ((N + len - 1) / len) < want_ctas) len >>= 1;
   return len;
 }
-
-size_t topk_select_ws_bytes(int nq, int64_t N, int k) {
-  if (N <= SELECT_SLICE || nq <= 0 || k <= 0) return 0;
+static size_t slice_ws_bytes(int nq, int64_t N, int k) {
+  if (N <= SELECT_SLICE) return 0;
   const int64_t len = select_slice_len(nq, N);
   return align_up(size_t(nq) * size_t((N + len - 1) / len) * size_t(k) * 8, 256);
+}
+
+static size_t stream_smem_bytes(int k, int trig) {
+  return size_t(STREAM_STAGES) * STREAM_TRIP * 4 + size_t(trig + STREAM_TRIP + next_pow2(k)) * 8;
+}
+
+// Balanced runs pay off once a row is a few dozen trips long (a row costs a threshold bootstrap and a final select) and
+// the matrix is a few MB; smaller problems stay with one CTA per row.
+static bool stream_plan(int nq, int64_t N, int k, StreamPlan& p) {
+  if (N < 32 * STREAM_TRIP || int64_t(nq) * N < (int64_t(1) << 22)) return false;
+  const int64_t tpr = (N + STREAM_TRIP - 1) / STREAM_TRIP;
+  const int64_t units = int64_t(nq) * tpr;
+  if (units > (int64_t(1) << 30)) return false;
+  p.trig = std::min(4096, std::max(256, 4 * k));
+  const int per_sm = stream_smem_bytes(k, p.trig) + 3 * 1024 <= (227 * 1024) / 2 ? 2 : 1;      // CTAs that fit an SM's shared memory
+  const int64_t slots = int64_t(per_sm) * sm_count();
+  p.tpr = int(tpr);
+  p.units = int(units);
+  p.seg_trips = int((units + slots - 1) / slots);
+  p.grid = int((units + p.seg_trips - 1) / p.seg_trips);
+  p.spr = int(std::min<int64_t>(p.grid, (tpr + p.seg_trips - 1) / p.seg_trips + 1));
+  return true;
+}
+
+size_t topk_select_ws_bytes(int nq, int64_t N, int k) {
+  if (nq <= 0 || k <= 0) return 0;
+  StreamPlan p;
+  const size_t stream = stream_plan(nq, N, k, p) ? align_up(size_t(nq) * size_t(p.spr) * size_t(k) * 8, 256) : 0;
+  return std::max(stream, slice_ws_bytes(nq, N, k));        // which path runs depends on the alignment of the rows
 }
 
 int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base, const int64_t* col_id,
                        float* out_score, int64_t* out_id, cudaStream_t stream, void* ws, size_t ws_bytes) {
   const int P = next_pow2(k);
-  const size_t need = topk_select_ws_bytes(nq, N, k);
+  const size_t smem_slice = size_t(SELECT_CAP + P) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(stream_smem_bytes(LRAG_MAX_K, 4096))));
+    LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (SELECT_CAP + LRAG_MAX_K) * 8));
+    attr_set = true;
+  }
+  uint64_t* keys = static_cast<uint64_t*>(ws);
+  StreamPlan plan{};
+  const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15) == 0 && ld % 4 == 0;      // bulk copies need 16-byte aligned rows
+  if (aligned && ws && stream_plan(nq, N, k, plan) && ws_bytes >= size_t(nq) * size_t(plan.spr) * size_t(k) * 8) {
+    prof_begin(stream, PROF_SELECT);
+    topk_stream_kernel<<<plan.grid, STREAM_THREADS, stream_smem_bytes(k, plan.trig), stream>>>(S, ld, N, k, col_id, plan, keys);
+    prof_end(stream);
+    LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, plan.spr, k, P, id_base, out_score, out_id, plan);
+    LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+    return LRAG_OK;
+  }
+  const size_t need = slice_ws_bytes(nq, N, k);
   if (need && ws && ws_bytes >= need && nq <= 65535) {
     const int64_t slice_len = select_slice_len(nq, N);
     const int nslices = int((N + slice_len - 1) / slice_len);
-    const size_t smem = size_t(SELECT_CAP + P) * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-      LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (SELECT_CAP + LRAG_MAX_K) * 8));
-      LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (SELECT_CAP + LRAG_MAX_K) * 8));
-      attr_set = true;
-    }
-    uint64_t* keys = static_cast<uint64_t*>(ws);
-    const bool vec = (reinterpret_cast<uintptr_t>(S) & 15) == 0 && ld % 4 == 0;      // 16-byte loads need aligned rows
     prof_begin(stream, PROF_SELECT);
-    if (vec) topk_slice_kernel<true><<<dim3(nslices, nq), SELECT_THREADS, smem, stream>>>(S, ld, N, k, P, col_id, slice_len, nslices, keys);
-    else topk_slice_kernel<false><<<dim3(nslices, nq), SELECT_THREADS, smem, stream>>>(S, ld, N, k, P, col_id, slice_len, nslices, keys);
+    topk_slice_kernel<<<dim3(nslices, nq), SELECT_THREADS, smem_slice, stream>>>(S, ld, N, k, P, col_id, slice_len, nslices, keys);
     prof_end(stream);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
-    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, nslices * k, k, P, id_base, out_score, out_id);
+    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, nslices, k, P, id_base, out_score, out_id, StreamPlan{});
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
     return LRAG_OK;
   }

@@ -94,14 +94,18 @@ def dense_workspace_bytes(N: int, d: int, nq: int, k: int) -> int:
 # ------------------------------------------------------------------------------------------------
 def topk_select(S: torch.Tensor, k: int, id_base: int = 0, col_id: Optional[torch.Tensor] = None):
     lib = _native.init(S.device.index)
-    S = _need(S, torch.float32, 2, "S")
+    if S.is_cuda and S.dtype == torch.float32 and S.dim() == 2 and S.stride(1) == 1 and S.stride(0) >= S.shape[1] and S.shape[0] > 1:
+        ld = S.stride(0)                      # a column window of a wider score matrix is read in place
+    else:
+        S = _need(S, torch.float32, 2, "S")
+        ld = S.shape[1]
     nq, N = S.shape
     if col_id is not None:
         col_id = _need(col_id, torch.int64, 2, "col_id")
     s, i = _out(nq, k, S.device)
     nbytes = lib.lrag_topk_select_workspace_bytes(nq, N, k)       # long rows are selected slice by slice
     ws = _ws(nbytes, S.device) if nbytes else None
-    check(lib.lrag_topk_select_f32(_ptr(S), N, nq, N, k, id_base, _ptr(col_id), _ptr(s), _ptr(i), _ptr(ws), nbytes, _stream()),
+    check(lib.lrag_topk_select_f32(_ptr(S), ld, nq, N, k, id_base, _ptr(col_id), _ptr(s), _ptr(i), _ptr(ws), nbytes, _stream()),
           "lrag_topk_select_f32")
     return s, i
 

@@ -44,7 +44,9 @@ def _bf16(x):
 def test_topk_select_matches_oracle(eng):
     rng = np.random.default_rng(0)
     # rows longer than 2^18 scores take the sliced single-pass path (slices + merge)
-    for nq, N, k in [(3, 1000, 100), (5, 37, 64), (2, 70000, 1024), (4, 100, 100), (1, 1, 1), (3, 700_001, 100), (2, 1_100_000, 1024)]:
+    for nq, N, k in [(3, 1000, 100), (5, 37, 64), (2, 70000, 1024), (4, 100, 100), (1, 1, 1), (3, 700_001, 100), (2, 1_100_000, 1024),
+                      # balanced runs of trips: runs that cross row ends, rows of a few trips, a 4-score last trip, whole-trip rows
+                      (300, 20_000, 100), (700, 8196, 10), (40, 131_072, 256), (9, 1_000_004, 1024), (1100, 8192, 3)]:
         S = rng.standard_normal((nq, N)).astype(np.float32)
         S[:, ::7] = S[:, :1]                      # plenty of exact ties -> lower id first
         s, i = eng.topk_select(torch.from_numpy(S).cuda(), k, id_base=1000)
@@ -53,9 +55,27 @@ def test_topk_select_matches_oracle(eng):
         np.testing.assert_array_equal(s.cpu().numpy(), D)
 
 
+def test_topk_select_column_window_of_a_wider_matrix(eng):
+    """Row stride != row length: 16-byte aligned rows whose length is not a multiple of four scores (the ragged end of the
+    streamed path), a window starting at an unaligned column (plain-load path), short last slices, runs of -inf."""
+    rng = np.random.default_rng(3)
+    W = rng.standard_normal((3, 800_000)).astype(np.float32)
+    W[:, ::5] = W[:, :1]
+    W[1, 1000:300_000] = -np.inf
+    W[2, :2048] = np.sort(W[2, :2048])        # first trip ascending: the bootstrap threshold sits at its very end
+    W[0, 50:] = -np.inf                       # fewer finite scores than k: the k-th best is -inf, lowest ids first
+    Wd = torch.from_numpy(W).cuda()
+    for c0, N, k in [(0, 799_997, 100), (0, 262_146, 7), (4, 524_289 + 2048, 256), (3, 700_000, 100), (0, 800_000, 1000), (8, 270_001, 1),
+                     (0, 300_000, 257)]:
+        s, i = eng.topk_select(Wd[:, c0:c0 + N], k, id_base=5)
+        D, I = odense.topk_rows(W[:, c0:c0 + N], k, id_base=5)
+        np.testing.assert_array_equal(i.cpu().numpy(), I, err_msg=f"c0={c0} N={N} k={k}")
+        np.testing.assert_array_equal(s.cpu().numpy(), D, err_msg=f"c0={c0} N={N} k={k}")
+
+
 def test_topk_select_with_col_ids_and_skips(eng):
     rng = np.random.default_rng(1)
-    for nq, C, k, pool in [(4, 300, 50, 10000), (2, 600_000, 100, 5_000_000)]:      # the second shape is sliced
+    for nq, C, k, pool in [(4, 300, 50, 10000), (2, 600_000, 100, 5_000_000), (300, 20_000, 64, 100_000)]:      # the last two are streamed
         S = rng.standard_normal((nq, C)).astype(np.float32)
         ids = np.stack([rng.permutation(pool)[:C] for _ in range(nq)]).astype(np.int64)
         ids[:, 5::11] = -1

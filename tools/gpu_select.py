@@ -3,7 +3,10 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from legal_rag_b200 import engine
-for nq, N, k in [(64, 1_000_000, 100), (256, 1_000_000, 100), (8, 50_000_000, 100), (4096, 20_000, 100), (64, 1_000_000, 1000)]:
+SHAPES = [(64, 1_000_000, 100), (256, 1_000_000, 100), (8, 50_000_000, 100), (4096, 20_000, 100), (64, 1_000_000, 1000)]
+if len(sys.argv) == 4:          # one shape (for an ncu capture): nq N k
+    SHAPES = [tuple(int(a) for a in sys.argv[1:4])]
+for nq, N, k in SHAPES:
     S = torch.randn((nq, N), device="cuda")
     for _ in range(3):
         engine.topk_select(S, k)
