@@ -89,7 +89,10 @@ int lrag_dense_topk_bf16_ref(const void* X, int64_t N, int d, const void* Q, int
  * of each row are live).  Replaces the `sorted(range(N), key=scores[i], reverse=True)[:k]`
  * of legalrag/retrieval/bm25_retriever.py:75 for small corpora and ranks MaxSim
  * candidate scores.  If `col_id` is non-NULL ([nq, N] int64) the returned id is
- * col_id[row, col] (entries with col_id < 0 are skipped); else id_base + col. */
+ * col_id[row, col] (entries with col_id < 0 are skipped); else id_base + col.
+ * With a workspace of lrag_topk_select_workspace_bytes() long rows are streamed once by a
+ * one-wave grid (per-CTA candidate lists in the workspace, then a merge); without one
+ * (ws NULL) every row is selected by a single CTA. */
 size_t lrag_topk_select_workspace_bytes(int nq, int64_t N, int k);
 int lrag_topk_select_f32(const float* S, int64_t ld, int nq, int64_t N, int k, int64_t id_base,
                          const int64_t* col_id, float* out_score, int64_t* out_id, void* ws,
