@@ -655,6 +655,16 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+def with_burst(roof, peaks):
+    """Tensor-bound rooflines are quoted against the sustained cuBLAS figure (the kernel runs inside a long, power-capped
+    step); the same achieved rate against the burst figure is reported next to it -- a stage that follows a cooler stage
+    (the dense scan inside the hybrid step) runs at clocks between the two and can exceed the sustained number."""
+    if roof.get("bound") == "tensor":
+        roof["peak_burst"] = peaks["bf16_tflops_burst"]
+        roof["frac_of_burst"] = roof["achieved"] / peaks["bf16_tflops_burst"]
+    return roof
+
+
 def release(wl):
     """Drops a workload's device stores (the CPU leg only needs its shape attributes)."""
     import gc
@@ -729,7 +739,7 @@ def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks):
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / steps},
             "gpu_launches": launches,
-            "roofline": wl.roofline(kernel_ms, peaks),
+            "roofline": with_burst(wl.roofline(kernel_ms, peaks), peaks),
             "global_queries_per_s": wl.nq * steps / (ms * 1e-3)}
 
 
