@@ -637,22 +637,35 @@ def run_reference(args, rank, world):
     installable here) on the host cores."""
     if rank != 0:
         return
-    wl = WORKLOADS[args.workload](args, 0, 1, None)
-    run, sample = wl.cpu_sample()
-    for _ in range(max(1, min(args.warmup, 2))):
-        run()
-    vals, t = [], 0.0
-    for _ in range(args.steps):
-        v, dt = run()
-        vals.append(v); t += dt
-    value = len(vals) / sum(1.0 / v for v in vals)   # harmonic mean == total queries / total time
+    def timed(name):
+        wl = WORKLOADS[name](args, 0, world, None)      # same config object as the native arm at this world size
+        run, sample = wl.cpu_sample()
+        for _ in range(max(1, min(args.warmup, 2))):
+            run()
+        vals, t = [], 0.0
+        for _ in range(args.steps):
+            v, dt = run()
+            vals.append(v); t += dt
+        value = len(vals) / sum(1.0 / v for v in vals)   # harmonic mean == total queries / total time
+        return wl, value, 1e3 * t / args.steps, sample
+
+    # A host answers N shards one after the other: N times the work in N times the time, so the metric's
+    # "rank-level query scans per second" does not depend on N for the CPU path.
+    wl, value, ms, sample = timed(args.workload)
     cores = getattr(wl, "cpu_cores", os.cpu_count())
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
-                      "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if args.workload == "dense" and not args.no_hybrid_block and not (args.n_docs or args.dim or args.nq):
+        wl_h, v_h, ms_h, sample_h = timed("hybrid")      # the counterpart of the native arm's "hybrid" object
+        line["hybrid"] = {"value": v_h, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "ms_per_step": ms_h, "config": wl_h.config(),
+                          "cpu_baseline": {"value": v_h, "unit": UNIT, "cores": getattr(wl_h, "cpu_cores", os.cpu_count()), "kind": "port",
+                                           "sample": sample_h},
+                          "e2e": {"value": v_h, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
 
 
 def with_burst(roof, peaks):
