@@ -3,102 +3,126 @@
 // filter :309-310, slice :384 of the reference; restated in oracle/fuse.py, which is pinned to
 // outputs of the reference's own code in tests/golden/fuse_golden.json).
 //
-// Tiny and latency-bound: <= 3 * kc candidates per query live in shared memory for the whole pass
-// (load -> per-channel min/max -> union by id with per-candidate channel lookups -> RRF min/max ->
-// score -> filter -> bitonic sort by (score desc, id asc) -> top-k + breakdown).  Arithmetic is
-// fp64 like the reference's Python floats; only the stored scores are fp32.
+// <= 3 * kc candidates per query live in shared memory for the whole pass:
+//   load -> per-channel min/max (one fused reduction) -> id -> {position in each channel} through a
+//   shared-memory hash table (the reference's dict lookups; a linear search here made the pass
+//   quadratic in kc) -> RRF min/max -> score -> filter -> bitonic sort of packed 64-bit keys
+//   (ord32(score) << 32 | ~entry; equal scores fall back to comparing the int64 ids) -> top-k + breakdown.
+// Arithmetic is fp64 like the reference's Python floats; only the stored scores are fp32.
 #include "common.cuh"
 
 namespace lrag {
 
 constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_WARPS = FUSE_THREADS / 32;
+constexpr int FUSE_NONE = 0x7fffffff;
 
 struct FuseParams {
   const float* s[3]; const int64_t* i[3];
-  int nq, kc, k, method, rrf_k, P;    // P = pow2 >= 3*kc
+  int nq, kc, k, method, rrf_k, P, H;    // P = pow2 >= 3*kc (sort width), H = pow2 hash slots (>= 4/3 of the entries)
   double w[3]; double alpha; double min_final;
   float* out_score; int64_t* out_id; float* out_breakdown;
 };
 
-__device__ __forceinline__ double block_reduce(double v, bool is_max, double* scratch) {
+// Block-wide min of v[0..NV/2) and max of v[NV/2..NV) in one pass (every thread gets the results back in v).
+template <class T, int NV>
+__device__ __forceinline__ void block_minmax(T (&v)[NV], T (*scratch)[NV]) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double other = __shfl_xor_sync(0xffffffffu, v, o);
-    v = is_max ? fmax(v, other) : fmin(v, other);
+  for (int j = 0; j < NV; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const T other = __shfl_xor_sync(0xffffffffu, v[j], o);
+      v[j] = j < NV / 2 ? min(v[j], other) : max(v[j], other);
+    }
   }
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) scratch[threadIdx.x >> 5][j] = v[j];
   __syncthreads();
-  double r = scratch[0];
-  for (int w = 1; w < FUSE_THREADS / 32; ++w) r = is_max ? fmax(r, scratch[w]) : fmin(r, scratch[w]);
-  __syncthreads();
-  return r;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    T r = scratch[0][j];
+#pragma unroll
+    for (int w = 1; w < FUSE_WARPS; ++w) r = j < NV / 2 ? min(r, scratch[w][j]) : max(r, scratch[w][j]);
+    v[j] = r;
+  }
+}
+
+__device__ __forceinline__ uint32_t fuse_hash(int64_t id, int H) {
+  return uint32_t((uint64_t(id) * 0x9E3779B97F4A7C15ull) >> 40) & uint32_t(H - 1);
 }
 
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_kernel(const FuseParams p) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  const int kc = p.kc, n3 = 3 * kc, P = p.P;
-  int64_t* ids = reinterpret_cast<int64_t*>(sm_raw);                   // [3*kc]
-  double* rrf_tot = reinterpret_cast<double*>(ids + n3);               // [3*kc]
-  double* wsum = rrf_tot + n3;                                         // [3*kc]
-  double* score = wsum + n3;                                           // [P]  (sort key, -inf = dropped)
-  float* sc = reinterpret_cast<float*>(score + P);                     // [3*kc]
-  int* order = reinterpret_cast<int*>(sc + n3);                        // [P]
-  uint8_t* owns = reinterpret_cast<uint8_t*>(order + P);               // [3*kc] entry owns its id
-  __shared__ double scratch[FUSE_THREADS / 32];
+  const int kc = p.kc, n3 = 3 * kc, P = p.P, H = p.H;
+  int64_t* ids = reinterpret_cast<int64_t*>(sm_raw);                                   // [3*kc]
+  double* rrf_tot = reinterpret_cast<double*>(ids + n3);                               // [3*kc]
+  double* wsum = rrf_tot + n3;                                                         // [3*kc]
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(wsum + n3);         // [P] sort keys (0 = dropped)
+  unsigned long long* hkey = skey + P;                                                 // [H] hash slots: id, ~0 = empty
+  int* hpos = reinterpret_cast<int*>(hkey + H);                                        // [H][3] first position of the id in each channel
+  float* sc = reinterpret_cast<float*>(hpos + 3 * H);                                  // [3*kc]
+  __shared__ double scratch[FUSE_WARPS][6];
   __shared__ int nvalid[3];
-  __shared__ double lo[3], hi[3];
 
   const int q = blockIdx.x, tid = threadIdx.x;
   if (tid < 3) nvalid[tid] = 0;
+  for (int h = tid; h < H; h += FUSE_THREADS) { hkey[h] = ~0ull; hpos[3 * h] = hpos[3 * h + 1] = hpos[3 * h + 2] = FUSE_NONE; }
   __syncthreads();
   // ---- load; valid entries of a channel form a prefix (id == -1 padding at the tail) ----
   for (int e = tid; e < n3; e += FUSE_THREADS) {
-    const int ch = e / kc, pos = e % kc;
+    const int ch = e / kc, pos = e - ch * kc;
     int64_t id = -1; float s = 0.f;
     if (p.i[ch]) { id = p.i[ch][size_t(q) * kc + pos]; s = p.s[ch][size_t(q) * kc + pos]; }
     ids[e] = id; sc[e] = s;
-    if (id >= 0) atomicMax(&nvalid[ch], pos + 1);
+    // the last valid entry of a channel is followed by padding (or by the end of the list): few threads reach the atomic
+    if (id >= 0 && (pos == kc - 1 || p.i[ch][size_t(q) * kc + pos + 1] < 0)) atomicMax(&nvalid[ch], pos + 1);
   }
   __syncthreads();
-  // ---- per-channel min / max (hybrid_retriever.py:24-30) ----
-  for (int ch = 0; ch < 3; ++ch) {
-    double mn = INFINITY, mx = -INFINITY;
-    for (int pos = tid; pos < nvalid[ch]; pos += FUSE_THREADS) {
-      const double v = double(sc[ch * kc + pos]);
-      mn = fmin(mn, v); mx = fmax(mx, v);
-    }
-    mn = block_reduce(mn, false, scratch);
-    mx = block_reduce(mx, true, scratch);
-    if (tid == 0) { lo[ch] = mn; hi[ch] = mx; }
-  }
-  __syncthreads();
-  // ---- union by id: the first channel holding an id owns it ----
-  double rmn = INFINITY, rmx = -INFINITY;
-  for (int e = tid; e < P; e += FUSE_THREADS) {
-    if (e < P) { score[e] = -INFINITY; order[e] = e; }
-    if (e >= n3) continue;
-    const int ch = e / kc, pos = e % kc;
+  // ---- per-channel min / max (hybrid_retriever.py:24-30) and the id table, one pass ----
+  float mm[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};     // fp32 inputs: their min / max are exact in fp32
+  for (int e = tid; e < n3; e += FUSE_THREADS) {
+    const int ch = e / kc, pos = e - ch * kc;
+    if (pos >= nvalid[ch]) continue;
+    const float v = sc[e];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (c == ch) { mm[c] = fminf(mm[c], v); mm[3 + c] = fmaxf(mm[3 + c], v); }
     const int64_t id = ids[e];
-    bool own = (id >= 0) && pos < nvalid[ch];
-    int at[3] = {-1, -1, -1};
-    if (own) {
-      at[ch] = pos;
-      for (int c = 0; c < 3 && own; ++c) {
-        if (c == ch) continue;
-        int found = -1;
-        for (int j = 0; j < nvalid[c]; ++j) if (ids[c * kc + j] == id) { found = j; break; }
-        if (found >= 0 && c < ch) own = false;
-        at[c] = found;
-      }
+    if (id < 0) continue;
+    uint32_t h = fuse_hash(id, H);
+    for (;;) {
+      const unsigned long long prev = atomicCAS(&hkey[h], ~0ull, (unsigned long long)id);
+      if (prev == ~0ull || prev == (unsigned long long)id) break;
+      h = (h + 1) & uint32_t(H - 1);
     }
-    owns[e] = own ? 1 : 0;
-    if (!own) { rrf_tot[e] = 0.0; wsum[e] = 0.0; continue; }
+    atomicMin(&hpos[3 * h + ch], pos);
+  }
+  block_minmax<float, 6>(mm, reinterpret_cast<float (*)[6]>(&scratch[0][0]));
+  const double lo[3] = {double(mm[0]), double(mm[1]), double(mm[2])}, hi[3] = {double(mm[3]), double(mm[4]), double(mm[5])};
+  __syncthreads();            // table complete
+  // ---- union by id: the first channel holding an id owns it (its first occurrence there) ----
+  double rr[2] = {INFINITY, -INFINITY};
+  for (int e = tid; e < P; e += FUSE_THREADS) {
+    skey[e] = 0ull;
+    if (e >= n3) continue;
+    const int ch = e / kc, pos = e - ch * kc;
+    const int64_t id = ids[e];
+    rrf_tot[e] = 0.0; wsum[e] = __longlong_as_double(0x7ff8000000000000ll);       // NaN marks "not an owner"
+    if (id < 0 || pos >= nvalid[ch]) continue;
+    uint32_t h = fuse_hash(id, H);
+    while (hkey[h] != (unsigned long long)id) h = (h + 1) & uint32_t(H - 1);
+    const int at[3] = {hpos[3 * h], hpos[3 * h + 1], hpos[3 * h + 2]};
+    bool own = at[ch] == pos;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c < ch && at[c] != FUSE_NONE) own = false;
+    if (!own) continue;
     double tot = 0.0, ws = 0.0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (at[c] < 0) continue;
+      if (at[c] == FUSE_NONE) continue;
       const double wr = (p.method == 2) ? p.w[c] : 1.0;
       tot += wr * (1.0 / double(p.rrf_k + at[c] + 1));
       const double range = hi[c] - lo[c];
@@ -106,61 +130,65 @@ fuse_kernel(const FuseParams p) {
       ws += p.w[c] * nv;
     }
     rrf_tot[e] = tot; wsum[e] = ws;
-    rmn = fmin(rmn, tot); rmx = fmax(rmx, tot);
+    rr[0] = fmin(rr[0], tot); rr[1] = fmax(rr[1], tot);
   }
-  rmn = block_reduce(rmn, false, scratch);
-  rmx = block_reduce(rmx, true, scratch);
-  const double rrange = rmx - rmn;
-  // ---- score per method, min_final_score filter ----
+  block_minmax<double, 2>(rr, reinterpret_cast<double (*)[2]>(&scratch[0][0]));
+  const double rmn = rr[0], rrange = rr[1] - rr[0];
+  // ---- score per method, min_final_score filter, sort key ----
   for (int e = tid; e < n3; e += FUSE_THREADS) {
-    if (!owns[e]) continue;
+    if (!(wsum[e] == wsum[e])) continue;
     const double rn = (rrange < 1e-12) ? 0.0 : (rrf_tot[e] - rmn) / rrange;
     double s;
     if (p.method == 0) s = wsum[e];
     else if (p.method == 3) s = p.alpha * rn + (1.0 - p.alpha) * wsum[e];
     else s = rn;
     // rank on the value that is returned (fp32), so equal outputs are ordered by id
-    if (s >= p.min_final) score[e] = double(float(s));
+    if (s >= p.min_final) skey[e] = ((unsigned long long)ord32(float(s) + 0.0f) << 32) | (unsigned long long)(0xffffffffu - uint32_t(e));   // + 0: no -0
   }
   __syncthreads();
-  // ---- bitonic sort of entry indices by (score desc, id asc); dropped entries sink ----
+  // ---- bitonic sort by (score desc, id asc); dropped entries (key 0) sink ----
+  auto before = [&](unsigned long long a, unsigned long long b) {
+    if ((a ^ b) >> 32) return a > b;                                   // different scores (or one of them dropped)
+    if (a == 0ull || b == 0ull) return false;
+    return ids[0xffffffffu - uint32_t(a)] < ids[0xffffffffu - uint32_t(b)];       // same fp32 score: lower id first
+  };
+  // Pair i of a step touches elements l = 2i - (i & (stride - 1)) and l + stride: for stride <= 32 the 32 pairs of a
+  // warp stay inside one aligned 64-element block, so consecutive steps with stride <= 32 only need a warp barrier.
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int i = tid; i < P / 2; i += FUSE_THREADS) {
         const int l = 2 * i - (i & (stride - 1)), h = l + stride;
-        const int a = order[l], b = order[h];
-        const double sa = score[a], sb = score[b];
-        const int64_t ia = a < n3 ? ids[a] : -1, ib = b < n3 ? ids[b] : -1;
-        const bool a_first = sa > sb || (sa == sb && ia >= 0 && (ib < 0 || ia < ib));
-        const bool b_first = sb > sa || (sa == sb && ib >= 0 && (ia < 0 || ib < ia));
+        const unsigned long long a = skey[l], b = skey[h];
         const bool desc = ((l & size) == 0);
-        if (desc ? b_first : a_first) { order[l] = b; order[h] = a; }
+        if (desc ? before(b, a) : before(a, b)) { skey[l] = b; skey[h] = a; }
       }
-      __syncthreads();
+      const int next = stride > 1 ? stride >> 1 : size;       // stride of the step that follows (size = 2 * size / 2)
+      if (stride > 32 || next > 32) __syncthreads(); else __syncwarp();
     }
   }
+  __syncthreads();
   // ---- top-k + breakdown ----
   for (int r = tid; r < p.k; r += FUSE_THREADS) {
-    const int e = (r < P) ? order[r] : -1;
-    const bool ok = e >= 0 && e < n3 && owns[e] && score[e] > -INFINITY;
+    const unsigned long long key = (r < P) ? skey[r] : 0ull;
     float* os = p.out_score + size_t(q) * p.k + r;
     int64_t* oi = p.out_id + size_t(q) * p.k + r;
     float* bd = p.out_breakdown ? p.out_breakdown + (size_t(q) * p.k + r) * 8 : nullptr;
-    if (!ok) {
+    if (key == 0ull) {
       *os = LRAG_PAD_SCORE; *oi = -1;
       if (bd) for (int j = 0; j < 8; ++j) bd[j] = 0.f;
       continue;
     }
+    const int e = int(0xffffffffu - uint32_t(key));
     const int64_t id = ids[e];
-    *os = float(score[e]); *oi = id;
+    *os = unord32(uint32_t(key >> 32)); *oi = id;
     if (!bd) continue;
-    const int ch = e / kc;
+    uint32_t h = fuse_hash(id, H);
+    while (hkey[h] != (unsigned long long)id) h = (h + 1) & uint32_t(H - 1);
     double norm[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
-      int found = -1;
-      if (c == ch) found = e % kc;
-      else for (int j = 0; j < nvalid[c]; ++j) if (ids[c * kc + j] == id) { found = j; break; }
-      if (found < 0) continue;
+      const int found = hpos[3 * h + c];
+      if (found == FUSE_NONE) continue;
       const double range = hi[c] - lo[c];
       norm[c] = (range < 1e-12) ? 0.0 : (double(sc[c * kc + found]) - lo[c]) / range;
       raw[c] = ((p.method == 2) ? p.w[c] : 1.0) * (1.0 / double(p.rrf_k + found + 1));
@@ -169,6 +197,7 @@ fuse_kernel(const FuseParams p) {
     const double rn = (rrange < 1e-12) ? 0.0 : (tot - rmn) / rrange;
     double contrib[3] = {0, 0, 0};
     const double mass = (p.method == 3) ? p.alpha * rn : ((p.method == 0) ? 0.0 : rn);
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
       if (p.method == 0) contrib[c] = p.w[c] * norm[c];
       else if (p.method == 3) contrib[c] = (1.0 - p.alpha) * p.w[c] * norm[c];
@@ -199,10 +228,11 @@ extern "C" int lrag_fuse_topk(const float* s_dense, const int64_t* i_dense, cons
   p.nq = nq; p.kc = kc; p.k = k; p.method = method; p.rrf_k = rrf_k;
   int P = 32; while (P < 3 * kc) P <<= 1;
   p.P = P;
+  p.H = P <= 1024 ? 2 * P : P;      // load factor <= 0.5 for the usual list lengths, <= 0.75 at kc = 1024 (shared memory)
   p.w[0] = w_dense; p.w[1] = w_bm25; p.w[2] = w_colb;
   p.alpha = alpha; p.min_final = min_final;
   p.out_score = out_score; p.out_id = out_id; p.out_breakdown = out_breakdown;
-  const size_t smem = size_t(3 * kc) * (8 + 8 + 8 + 4) + size_t(P) * (8 + 4) + size_t(3 * kc) + 16;
+  const size_t smem = size_t(3 * kc) * (8 + 8 + 8 + 4) + size_t(P) * 8 + size_t(p.H) * (8 + 12) + 16;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

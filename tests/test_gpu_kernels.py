@@ -386,6 +386,39 @@ def test_fuse_batch_matches_oracle_and_filters(eng):
                 check_topk_parity(s[q:q + 1], i[q:q + 1], O_s, O_i, 100, TAU_FP32, what=f"fuse-batch-{method}")
 
 
+def test_fuse_long_lists_wide_ids_and_ties(eng):
+    """kc = 1024 (the hash table at its highest load), ids above 2^32 (the sort key holds entry indices, not ids, so the
+    id order of equal scores must still hold), and channels full of equal scores."""
+    rng = np.random.default_rng(33)
+    cases = []
+    for q in range(6):
+        pool = rng.permutation(5000)[:2500].astype(np.int64) + (1 << 33) * (q % 2)
+        def lst(n, levels):
+            ids = rng.permutation(pool)[:n]
+            sc = np.sort(rng.integers(0, levels, n).astype(np.float32))[::-1]       # few distinct values: long tie runs
+            return [(int(a), float(b)) for a, b in zip(ids, sc)]
+        cases.append({"dense": lst(1024, 7), "bm25": lst(int(rng.integers(500, 1025)), 5), "colbert": lst(1024 if q < 3 else 0, 3)})
+    for method in ofuse.METHODS:
+        s, i, bd = _fuse_gpu(eng, cases, 1500, method=method)
+        s, i, bd = s.cpu().numpy(), i.cpu().numpy(), bd.cpu().numpy()
+        for q, c in enumerate(cases):
+            rows = ofuse.fuse(c["dense"], c["bm25"], c["colbert"], method=method)
+            m = min(len(rows), 1500)
+            got = [(int(a), float(b)) for a, b in zip(i[q, :m], s[q, :m])]
+            assert len({a for a, _ in got}) == m and (i[q, m:] == -1).all(), "ids are unique and the tail is padding"
+            want = {r["id"]: r["score"] for r in rows}
+            if m == len(rows):
+                assert {a for a, _ in got} == set(want)
+            for a, b in got:
+                assert abs(b - want[a]) <= 1e-5 * max(1.0, abs(want[a])), (method, q, a, b, want[a])
+            # output order: score descending, equal fp32 scores by ascending id
+            for (a0, b0), (a1, b1) in zip(got[:-1], got[1:]):
+                assert b0 > b1 or (b0 == b1 and a0 < a1), (method, q, (a0, b0), (a1, b1))
+            # nothing better was left out
+            if m < len(rows):
+                assert min(b for _, b in got) >= sorted(want.values(), reverse=True)[m - 1] - 1e-5
+
+
 def test_bm25_device_built_scale_model_matches_oracle(eng):
     """SURVEY 8d config 4's 50 000-doc / 5 000-term scale model, index built on the device by the bench's
     generator, scored by the kernel, checked against the fp64 oracle on the same postings."""
