@@ -352,6 +352,32 @@ def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None,
     return (merge or topk_merge)(cat_s, cat_i, k)
 
 
+def allgather_merge_many(lists, k: int, group=None, merge=None):
+    """allgather_merge for several channels at once: every rank's local lists [(scores [nq, k], ids [nq, k]), ...] travel in
+    ONE all-gather (packed bytes), then each channel is merged.  Ranks meet once per step instead of once per channel, so a
+    step costs max over ranks of the summed scan times rather than the sum of per-stage maxima."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return list(lists)
+    world = dist.get_world_size(group)
+    flat = [t.contiguous().view(torch.uint8).reshape(-1) for pair in lists for t in pair]
+    sizes = [f.numel() for f in flat]
+    mine = torch.cat(flat)
+    gathered = torch.empty((world, mine.numel()), dtype=torch.uint8, device=mine.device)
+    dist.all_gather_into_tensor(gathered.view(-1), mine, group=group)
+    out, off = [], 0
+    for n, (sc, ids) in enumerate(lists):
+        nq = sc.shape[0]
+        parts = []
+        for t in (sc, ids):
+            nb = sizes[len(parts) + 2 * n]
+            g = gathered[:, off:off + nb].contiguous().view(t.dtype).view(world, nq, k)
+            parts.append(g.permute(1, 0, 2).reshape(nq, world * k).contiguous())
+            off += nb
+        out.append((merge or topk_merge)(parts[0], parts[1], k))
+    return out
+
+
 @dataclass
 class HybridShard:
     """One rank's slice of the three stores plus the batched hybrid search over them:
@@ -381,18 +407,24 @@ class HybridShard:
         first-stage channel over the whole corpus like the reference (hybrid_retriever.py:299) -- every document of the
         shard is scored by the batched full-corpus kernel; needs one token row per document (no id aliasing)."""
         import torch.distributed as dist
-        ds, di = allgather_merge(*dense_topk(self.X, Qd, kc, self.id_base), kc, self.group)
-        bs, bi = allgather_merge(*bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc), kc, self.group)
+        # local scans first, one exchange for all channels afterwards
+        local = [dense_topk(self.X, Qd, kc, self.id_base), bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc)]
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, w_colbert=w_colbert, **fuse_kw)
-        if self.tokens is None or Qtok is None:
-            return fuse_topk((ds, di), (bs, bi), None, k=k, **kw)
-        if colbert_mode == "scan":
+        scan = colbert_mode == "scan" and self.tokens is not None and Qtok is not None
+        if scan:
             if self.tokens.shape[0] != self.X.shape[0] or self.tok_row_base != self.id_base:
                 raise LragError("colbert_mode='scan' needs one token row per document of the shard")
-            kk = min(kc, int(self.tokens.shape[0]))
-            cs, ci = maxsim_scan_topk(self.tokens, self.doclen, Qtok, kk, id_base=self.id_base)
-            cs, ci = allgather_merge(cs, ci, kk, self.group)
-            return fuse_topk((ds, di), (bs, bi), (cs, ci), k=k, **kw)
+            cs, ci = maxsim_scan_topk(self.tokens, self.doclen, Qtok, min(kc, int(self.tokens.shape[0])), id_base=self.id_base)
+            if cs.shape[1] < kc:          # a shard with fewer documents than kc: pad so that all lists travel together
+                cs = torch.nn.functional.pad(cs, (0, kc - cs.shape[1]), value=PAD_SCORE)
+                ci = torch.nn.functional.pad(ci, (0, kc - ci.shape[1]), value=-1)
+            local.append((cs, ci))
+        merged = allgather_merge_many(local, kc, self.group)
+        (ds, di), (bs, bi) = merged[0], merged[1]
+        if self.tokens is None or Qtok is None:
+            return fuse_topk((ds, di), (bs, bi), None, k=k, **kw)
+        if scan:
+            return fuse_topk((ds, di), (bs, bi), merged[2], k=k, **kw)
         # candidate set = every doc either channel returned, best fused first; -1 pads short rows
         _, cand_gid = fuse_topk((ds, di), (bs, bi), None, k=2 * kc, method=method, w_dense=w_dense, w_bm25=w_bm25)
         rows = torch.where(cand_gid >= 0, cand_gid % max(1, self.tok_rows_total), cand_gid) - self.tok_row_base

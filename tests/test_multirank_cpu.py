@@ -34,6 +34,14 @@ def _worker(rank, world, port, N, d, nq, k, out_dir):
     s, i = engine.allgather_merge(torch.from_numpy(D), torch.from_numpy(I), k, merge=merge)
     np.save(os.path.join(out_dir, f"s{rank}.npy"), s.numpy())
     np.save(os.path.join(out_dir, f"i{rank}.npy"), i.numpy())
+    # several channels in one packed all-gather (HybridShard's exchange): same lists as one all-gather per channel
+    Q2 = rng.standard_normal((nq, d)).astype(np.float32)
+    D2, I2 = odense.flat_ip_topk(Q2, X[lo:hi], k, id_base=lo)
+    many = engine.allgather_merge_many([(torch.from_numpy(D), torch.from_numpy(I)), (torch.from_numpy(D2), torch.from_numpy(I2))],
+                                       k, merge=merge)
+    one = engine.allgather_merge(torch.from_numpy(D2), torch.from_numpy(I2), k, merge=merge)
+    assert torch.equal(many[0][0], s) and torch.equal(many[0][1], i)
+    assert torch.equal(many[1][0], one[0]) and torch.equal(many[1][1], one[1])
     dist.destroy_process_group()
 
 
