@@ -67,8 +67,8 @@ topk_merge_kernel(const float* score, const int64_t* id, int L, int k, int P, fl
 // CTA then emits its list for the finished row and starts over.  Trips arrive through a shared-memory ring of 16 KB
 // stages filled by bulk asynchronous copies (cp.async.bulk, completion on mbarriers) that thread 0 keeps three trips
 // ahead of the filter, so the bytes in flight per SM do not depend on how the filter's barriers fall.  The filter is per
-// thread: a thread whose 16 scores stay below the threshold does nothing.  The first trip of a row sets a threshold
-// without a select: the k-th largest of the 256 per-thread maxima of the trip has k scores at or above it.
+// thread: a thread whose 8 scores stay below the threshold does nothing.  The first trip of a row sets a threshold
+// without streaming anything twice: the k-th largest of the 512 per-thread maxima of the trip has k scores at or above it.
 // topk_slice_kernel: the same filter over plain loads and fixed slices, for rows that are not 16-byte aligned.
 // ------------------------------------------------------------------------------------------------
 constexpr int64_t SELECT_SLICE = int64_t(1) << 18;      // scores per slice CTA (1 MB)
