@@ -564,6 +564,32 @@ def test_config0_ucc_hybrid_matches_reference_path(eng):
                               100, 2e-3, what=f"config0-{method}")
 
 
+def test_graphed_single_query_equals_eager_calls(eng):
+    """configs[0]'s online shape: one query at a time through a captured CUDA graph; replays with new inputs (short, long,
+    empty and out-of-vocabulary term lists) return exactly what the eager kernel calls return."""
+    import argparse
+    import bench
+    wl = bench.UccWorkload(argparse.Namespace(nq=16, k=100), 0, 1, torch.device("cuda", 0))
+    wl.setup()
+    docs, V, X, Q, queries = wl._corpus()
+    queries[3] = []                                   # no tokens: BM25 contributes zero scores only
+    queries[5] = [-1, -1, queries[5][0]]              # out-of-vocabulary tokens
+    queries[7] = (queries[7] * 8)[:32]                # as long as the graph allows, repeated tokens
+    g = eng.GraphedHybridQuery(wl.X, wl.index, k=100, nq=1, max_terms=32)
+    for q in list(range(16)) + [2, 0]:                # replays in any order, the same query twice
+        s, i = g.search(torch.from_numpy(Q[q:q + 1]), [queries[q]])
+        qi = torch.tensor([0, len(queries[q])], dtype=torch.int64).cuda()
+        qt = torch.tensor(queries[q] if queries[q] else [], dtype=torch.int32).cuda()
+        Qd = torch.from_numpy(Q[q:q + 1]).cuda().to(torch.bfloat16)
+        d = eng.dense_topk(wl.X, Qd, 100)
+        b = eng.bm25_topk(wl.index, qi, qt, max(1, len(queries[q])), 100)
+        es, ei = eng.fuse_topk(d, b, None, k=100, method="weighted_sum", w_dense=0.6, w_bm25=0.4)
+        np.testing.assert_array_equal(i.numpy(), ei.cpu().numpy(), err_msg=f"query {q}")
+        np.testing.assert_array_equal(s.numpy(), es.cpu().numpy(), err_msg=f"query {q}")
+    with pytest.raises(eng.LragError):
+        g.search(torch.from_numpy(Q[:1]), [[1] * 33])
+
+
 def test_bm25_kernel_reproduces_the_upstream_readme_example(eng):
     """The rank_bm25 README's published answer (see tests/test_oracle.py) through the CUDA path."""
     from legal_rag_b200.bm25_index import Bm25HostIndex
