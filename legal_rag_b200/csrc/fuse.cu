@@ -19,7 +19,7 @@ constexpr int FUSE_NONE = 0x7fffffff;
 
 struct FuseParams {
   const float* s[3]; const int64_t* i[3];
-  int nq, kc, k, method, rrf_k, P, H;    // P = pow2 >= 3*kc (sort width), H = pow2 hash slots (>= 4/3 of the entries)
+  int nq, kc, k, method, rrf_k, nch, P, H;    // nch = channels up to the last one present; P = pow2 >= nch*kc (sort width), H = pow2 hash slots
   double w[3]; double alpha; double min_final;
   float* out_score; int64_t* out_id; float* out_breakdown;
 };
@@ -56,8 +56,8 @@ __device__ __forceinline__ uint32_t fuse_hash(int64_t id, int H) {
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_kernel(const FuseParams p) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  const int kc = p.kc, n3 = 3 * kc, P = p.P, H = p.H;
-  int64_t* ids = reinterpret_cast<int64_t*>(sm_raw);                                   // [3*kc]
+  const int kc = p.kc, n3 = p.nch * kc, P = p.P, H = p.H;      // entries of absent trailing channels are not even laid out
+  int64_t* ids = reinterpret_cast<int64_t*>(sm_raw);                                   // [nch*kc]
   double* rrf_tot = reinterpret_cast<double*>(ids + n3);                               // [3*kc]
   double* wsum = rrf_tot + n3;                                                         // [3*kc]
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(wsum + n3);         // [P] sort keys (0 = dropped)
@@ -226,13 +226,14 @@ extern "C" int lrag_fuse_topk(const float* s_dense, const int64_t* i_dense, cons
   FuseParams p;
   p.s[0] = s_dense; p.s[1] = s_bm25; p.s[2] = s_colb; p.i[0] = i_dense; p.i[1] = i_bm25; p.i[2] = i_colb;
   p.nq = nq; p.kc = kc; p.k = k; p.method = method; p.rrf_k = rrf_k;
-  int P = 32; while (P < 3 * kc) P <<= 1;
+  p.nch = i_colb ? 3 : (i_bm25 ? 2 : 1);
+  int P = 32; while (P < p.nch * kc) P <<= 1;
   p.P = P;
   p.H = P <= 1024 ? 2 * P : P;      // load factor <= 0.5 for the usual list lengths, <= 0.75 at kc = 1024 (shared memory)
   p.w[0] = w_dense; p.w[1] = w_bm25; p.w[2] = w_colb;
   p.alpha = alpha; p.min_final = min_final;
   p.out_score = out_score; p.out_id = out_id; p.out_breakdown = out_breakdown;
-  const size_t smem = size_t(3 * kc) * (8 + 8 + 8 + 4) + size_t(P) * 8 + size_t(p.H) * (8 + 12) + 16;
+  const size_t smem = size_t(p.nch * kc) * (8 + 8 + 8 + 4) + size_t(P) * 8 + size_t(p.H) * (8 + 12) + 16;
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
