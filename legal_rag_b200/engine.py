@@ -470,9 +470,17 @@ class GraphedHybridQuery:
         self._h_i = torch.empty((nq, self.k), dtype=torch.int64).pin_memory()
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, **fuse_kw)
 
+        branch = torch.cuda.Stream(device=dev)
+
         def run():
+            # the two channels do not depend on each other: BM25 runs on a forked stream, so the captured graph has two
+            # branches that join at the fusion launch (critical path = the longer channel + fusion)
+            main = torch.cuda.current_stream(dev)
+            branch.wait_stream(main)
+            with torch.cuda.stream(branch):
+                b = bm25_topk(self.bm25, self.q_indptr, self.q_term, self.max_terms, self.k)
             d = dense_topk(self.X, self.Q, self.k, id_base)
-            b = bm25_topk(self.bm25, self.q_indptr, self.q_term, self.max_terms, self.k)
+            main.wait_stream(branch)
             return fuse_topk(d, b, None, k=self.k, **kw)
 
         side = torch.cuda.Stream(device=dev)
