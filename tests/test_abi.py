@@ -55,6 +55,20 @@ def test_library_is_sm100a_with_tcgen05_and_tma(lib_path):
     assert "UTMALDG" in sass, "no TMA tensor loads in the SASS"
 
 
+def test_select_workspace_sizing_needs_no_gpu(lib_path):
+    """The workspace queries are host arithmetic (the caller sizes its allocation before any launch): rows short enough
+    for one CTA each need none; long rows need room for every streaming CTA's k keys, a handful of lists per row."""
+    from legal_rag_b200 import _native
+    lib = _native.load()
+    assert lib.lrag_topk_select_workspace_bytes(4, 1000, 100) == 0
+    assert lib.lrag_topk_select_workspace_bytes(4096, 20_000, 100) == 0          # many medium rows: one CTA per row
+    for nq, N, k in [(64, 1_000_000, 100), (256, 1_000_000, 100), (8, 50_000_000, 100), (3, 700_001, 1024), (1, 4_200_000, 1)]:
+        b = lib.lrag_topk_select_workspace_bytes(nq, N, k)
+        assert b >= nq * k * 8 and b % 256 == 0
+        assert b <= 8 * (nq * k * 8) * max(1, 2 * 148 // nq + 2), (nq, N, k, b)     # bounded by lists of ~one wave of CTAs + slack
+    assert lib.lrag_topk_select_workspace_bytes(0, 10, 10) == 0
+
+
 def test_init_without_a_gpu_fails_loudly(lib_path):
     import torch
     if torch.cuda.is_available():
