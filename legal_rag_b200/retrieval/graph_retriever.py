@@ -67,56 +67,57 @@ class GraphRetriever:
                 self._id2row[str(aid)] = row
         self._snapshot = (id(chunks), len(chunks))
 
+    @staticmethod
+    def _article_id(obj: Any) -> str:
+        return str(getattr(obj, "article_id", None) or getattr(obj, "id", None) or "")
+
+    def _walk_params(self, top_k: int) -> Dict[str, Any]:
+        """The knobs of the graph walk and of the depth decay, with the reference's defaults (graph_retriever.py:98-108)."""
+        rcfg = getattr(self.cfg, "retrieval", None)
+        pick = lambda name, default: getattr(rcfg, name, default) if rcfg is not None else default      # noqa: E731
+        return {"depths": rcfg.graph_walk_depths if hasattr(rcfg, "graph_walk_depths") else {"default": 2},
+                "limit": int(pick("graph_limit", top_k * 8)), "rel_types": pick("graph_rel_types", None),
+                "min_conf": float(pick("graph_min_conf", 0.0)), "gamma": float(pick("graph_depth_gamma", 0.7))}
+
     def search(self, question: str, seeds: List[Any], *, decision: Any = None, lang: Optional[str] = None,
                top_k: int = 10) -> List[RetrievalHit]:
+        """Walk the graph from the seeds' articles, keep the neighbours the store knows (first visit of an article wins,
+        empty texts and other languages are dropped), score them against the question in one gathered inner-product
+        launch, weight by depth decay x relation weight x edge confidence, best first (graph_retriever.py:85-219)."""
         if self.graph is None:
             return []
         self._refresh()
-        rcfg = getattr(self.cfg, "retrieval", None)
-        eff_top_k = max(1, int(top_k))
-        relation_depths = rcfg.graph_walk_depths if hasattr(rcfg, "graph_walk_depths") else {"default": 2}
-        limit = int(getattr(rcfg, "graph_limit", eff_top_k * 8) if rcfg else eff_top_k * 8)
-        rel_types = getattr(rcfg, "graph_rel_types", None) if rcfg else None
-        min_conf = float(getattr(rcfg, "graph_min_conf", 0.0) if rcfg else 0.0)
-        gamma = float(getattr(rcfg, "graph_depth_gamma", 0.7) if rcfg else 0.7)
-
-        seed_ids: List[str] = []
-        for h in seeds or []:
-            c = getattr(h, "chunk", None)
-            if c is None:
-                continue
-            aid = getattr(c, "article_id", None) or getattr(c, "id", None)
+        depth_k = max(1, int(top_k))
+        knobs = self._walk_params(depth_k)
+        start = [aid for aid in (self._article_id(c) for c in (getattr(h, "chunk", None) for h in (seeds or [])) if c is not None)
+                 if aid]
+        if not start:
+            return []
+        visited = self.graph.walk(start_ids=start, relation_max_depth=knobs["depths"], limit=knobs["limit"],
+                                  rel_types=knobs["rel_types"], min_conf=knobs["min_conf"])
+        first_visit: Dict[str, Any] = {}
+        for node in visited or []:
+            aid = str(getattr(node, "article_id", "") or "").strip()
             if aid:
-                seed_ids.append(str(aid))
-        if not seed_ids:
-            return []
-        nodes = self.graph.walk(start_ids=seed_ids, relation_max_depth=relation_depths, limit=limit, rel_types=rel_types,
-                                min_conf=min_conf)
-        if not nodes:
-            return []
-        uniq: Dict[str, Any] = {}
-        for n in nodes:                                                     # :128-136
-            aid = str(getattr(n, "article_id", "") or "").strip()
-            if aid and aid not in uniq:
-                uniq[aid] = n
+                first_visit.setdefault(aid, node)
 
-        rows, kept, meta = [], [], []
-        for aid, n in uniq.items():                                         # :142-172
-            c = self.id2chunk.get(aid)
-            if not c or not (getattr(c, "text", "") or "").strip():
+        rows: List[int] = []
+        neighbours: List[tuple] = []           # (chunk copy tagged source="graph", depth, relations, edge confidence)
+        for aid, node in first_visit.items():
+            known = self.id2chunk.get(aid)
+            if not known or not (getattr(known, "text", "") or "").strip():
                 continue
-            if lang and (getattr(c, "lang", None) or "zh").strip().lower() != lang:
+            if lang and (getattr(known, "lang", None) or "zh").strip().lower() != lang:
                 continue
-            cc = copy.copy(c)
+            tagged = copy.copy(known)
             try:
-                setattr(cc, "source", "graph")
-            except Exception:
+                tagged.source = "graph"
+            except Exception:       # frozen models keep their source
                 pass
-            kept.append(cc)
+            edge_conf = float(((getattr(node, "meta", {}) or {}).get("_edge_conf", 1.0)) or 1.0)
+            neighbours.append((tagged, int(getattr(node, "graph_depth", 1) or 1), list(getattr(node, "relations", []) or []), edge_conf))
             rows.append(self._id2row[aid])
-            meta.append((int(getattr(n, "graph_depth", 1) or 1), list(getattr(n, "relations", []) or []),
-                         float(((getattr(n, "meta", {}) or {}).get("_edge_conf", 1.0)) or 1.0)))
-        if not kept:
+        if not neighbours:
             return []
 
         # the reference embeds the question as a passage here (no query instruction, :177) and divides by the
@@ -125,17 +126,17 @@ class GraphRetriever:
         qvec = qvec / (float(np.linalg.norm(qvec)) + 1e-9)
         X = self.store.index.matrix
         Q = torch.from_numpy(qvec[None, :]).to(X.device).to(torch.bfloat16)
-        sem = engine.gather_scores(X, Q, torch.tensor([rows], dtype=torch.int64, device=X.device))[0].cpu().numpy()
+        cosines = engine.gather_scores(X, Q, torch.tensor([rows], dtype=torch.int64, device=X.device))[0].cpu().tolist()
 
         hits: List[RetrievalHit] = []
-        for i, (c, s, (gd, rels, conf)) in enumerate(zip(kept, sem, meta), start=1):
-            dd, rw = _depth_decay(gd, gamma=gamma), _relation_weight(rels)
-            final = float(s) * dd * rw * conf
-            hits.append(RetrievalHit(chunk=c, score=final, rank=i, source="graph",
-                                     score_breakdown={"channel": "graph", "semantic": float(s), "depth_decay": dd,
-                                                      "relation_weight": rw, "edge_conf": conf, "final": final,
-                                                      "graph_depth": gd, "relations": rels}))
-        hits.sort(key=lambda h: float(h.score or 0.0), reverse=True)        # stable, like :211
-        for r, h in enumerate(hits, start=1):
-            h.rank = r
-        return hits[:eff_top_k]
+        for cos, (chunk, depth, relations, edge_conf) in zip(cosines, neighbours):
+            decay, rel_w = _depth_decay(depth, gamma=knobs["gamma"]), _relation_weight(relations)
+            value = float(cos) * decay * rel_w * edge_conf
+            hits.append(RetrievalHit(chunk=chunk, score=value, rank=0, source="graph",
+                                     score_breakdown={"channel": "graph", "semantic": float(cos), "depth_decay": decay,
+                                                      "relation_weight": rel_w, "edge_conf": edge_conf, "final": value,
+                                                      "graph_depth": depth, "relations": relations}))
+        hits.sort(key=lambda h: -float(h.score or 0.0))                     # stable, like the reference's sort (:211)
+        for pos, h in enumerate(hits):
+            h.rank = pos + 1
+        return hits[:depth_k]

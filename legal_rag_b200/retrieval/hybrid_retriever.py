@@ -24,50 +24,69 @@ CHANNELS = ("dense", "bm25", "colbert")
 
 
 def _as_channel_list(x: Any) -> List[str]:
+    """score_breakdown["channel"] in any of the shapes the reference tolerates -> list of names."""
     if x is None:
         return []
-    if isinstance(x, (list, set, tuple)):
-        return [str(i) for i in x]
-    return [str(x)]
+    return [str(v) for v in x] if isinstance(x, (list, set, tuple)) else [str(x)]
+
+
+def _by_score(hits: List[RetrievalHit]) -> List[RetrievalHit]:
+    """In-place: best score first (stable), ranks 1..n."""
+    hits.sort(key=lambda h: -float(h.score))
+    for pos, h in enumerate(hits):
+        h.rank = pos + 1
+    return hits
 
 
 def _dedup_keep_best(hits: List[RetrievalHit]) -> List[RetrievalHit]:
-    """Best-scoring hit per chunk.id, channels united, channel_contrib summed, re-ranked
-    (hybrid_retriever.py:71-130)."""
-    best: Dict[str, RetrievalHit] = {}
+    """One hit per chunk id (hybrid_retriever.py:71-130 of the reference, checked against its output in
+    tests/golden/fuse_golden.json): the occurrence with the highest score represents the chunk (the earliest one on equal
+    scores) and inherits the provenance of all of them -- the union of their `channel` lists and the per-channel sum of
+    their `channel_contrib` dicts; channels are listed by summed contribution (by name when there is none).  Chunks come
+    out best score first, in first-appearance order on ties."""
+    occurrences: Dict[str, List[RetrievalHit]] = {}
     for h in hits:
-        cid = h.chunk.id
-        sb = h.score_breakdown or {}
-        if cid not in best:
-            if "channel" in sb:
-                sb["channel"] = _as_channel_list(sb.get("channel"))
-                h.score_breakdown = sb
-            best[cid] = h
-            continue
-        b = best[cid]
-        sb_best = b.score_breakdown or {}
-        merged_channels = list(set(_as_channel_list(sb_best.get("channel"))) | set(_as_channel_list(sb.get("channel"))))
-        merged_contrib: Dict[str, float] = {}
-        for src in (sb_best.get("channel_contrib", {}) or {}, sb.get("channel_contrib", {}) or {}):
-            if isinstance(src, dict):
-                for k, v in src.items():
-                    merged_contrib[str(k)] = merged_contrib.get(str(k), 0.0) + float(v)
-        if float(h.score) > float(b.score):
-            best[cid] = h
-        rep = best[cid]
-        sb_rep = rep.score_breakdown or {}
-        if merged_contrib:
-            merged_channels.sort(key=lambda c: float(merged_contrib.get(c, 0.0)), reverse=True)
-            sb_rep["channel_contrib"] = merged_contrib
+        occurrences.setdefault(h.chunk.id, []).append(h)
+    kept: List[RetrievalHit] = []
+    for group in occurrences.values():
+        rep = group[0]
+        for h in group[1:]:
+            if float(h.score) > float(rep.score):
+                rep = h
+        info = rep.score_breakdown or {}
+        if len(group) == 1:
+            if "channel" in info:
+                info["channel"] = _as_channel_list(info["channel"])
+                rep.score_breakdown = info
         else:
-            merged_channels.sort()
-        sb_rep["channel"] = merged_channels
-        rep.score_breakdown = sb_rep
-    out = list(best.values())
-    out.sort(key=lambda x: float(x.score), reverse=True)
-    for i, h in enumerate(out, start=1):
-        h.rank = i
-    return out
+            names: Set[str] = set()
+            share: Dict[str, float] = {}
+            for h in group:
+                sb = h.score_breakdown or {}
+                names.update(_as_channel_list(sb.get("channel")))
+                part = sb.get("channel_contrib") or {}
+                if isinstance(part, dict):
+                    for name, value in part.items():
+                        share[str(name)] = share.get(str(name), 0.0) + float(value)
+            if share:
+                info["channel_contrib"] = share
+            info["channel"] = sorted(names, key=lambda c: (-share.get(c, 0.0), c)) if share else sorted(names)
+            rep.score_breakdown = info
+        kept.append(rep)
+    return _by_score(kept)
+
+
+class _Laps:
+    """Wall-clock laps of one search() for the reference's timing log line."""
+
+    def __init__(self) -> None:
+        self.t = {"start": time.time()}
+
+    def mark(self, name: str) -> None:
+        self.t[name] = time.time()
+
+    def ms(self, a: str, b: str) -> int:
+        return int((self.t[b] - self.t[a]) * 1000) if a in self.t and b in self.t else 0
 
 
 @dataclass
@@ -77,134 +96,108 @@ class HybridRetriever:
     def __post_init__(self) -> None:
         self.dense = DenseRetriever(self.cfg)
         self.bm25 = BM25Retriever(self.cfg)
-        self.colbert = None
+        self.colbert = None      # optional channel (hybrid_retriever.py:163-169): a failing init only disables it
         if getattr(self.cfg.retrieval, "enable_colbert", False):
             try:
                 self.colbert = ColBERTRetriever.from_config(self.cfg)
-            except Exception as e:                       # hybrid_retriever.py:163-169: the channel is optional
-                print("[HybridRetriever] ColBERT init failed:", repr(e))
+            except Exception as exc:
+                print("[HybridRetriever] ColBERT init failed:", repr(exc))
                 traceback.print_exc()
-                self.colbert = None
         self.graph = None        # plug a retrieval.GraphRetriever(cfg, graph=<graph store with walk()>) in here: the graph
                                  # store is host-side and injected, its scoring stage runs on the GPU
         self.reranker = None     # optional callable(question, hits) -> hits (cross-encoder rerank is out of scope)
 
     # ------------------------------------------------------------------ per-channel APIs
-    def search_dense(self, question: str, top_k: int = 10) -> List[RetrievalHit]:
-        top_k = max(1, int(top_k))
-        hits = self.dense.search(question, top_k)
-        hits.sort(key=lambda h: float(h.score), reverse=True)
-        for i, h in enumerate(hits, start=1):
-            h.rank = i
+    @staticmethod
+    def _label(hits: List[RetrievalHit], channel: str, raw_key: Optional[str], replace: bool) -> List[RetrievalHit]:
+        """What every per-channel API of the reference does to its hits (hybrid_retriever.py:172-279): order by score,
+        rank, source = "retriever", and a breakdown that names the channel (plus the raw score under `raw_key`).  The
+        dense channel replaces whatever breakdown the hit carried; the others keep it and fill in what is missing."""
+        for h in _by_score(hits):
             h.source = "retriever"
-            h.score_breakdown = {"channel": ["dense"], "dense_raw": float(h.score)}
+            if replace:
+                h.score_breakdown = {"channel": [channel], raw_key: float(h.score)}
+                continue
+            sb = h.score_breakdown or {}
+            sb["channel"] = _as_channel_list(sb.get("channel")) or [channel]
+            if raw_key:
+                sb.setdefault(raw_key, float(h.score))
+            h.score_breakdown = sb
         return hits
+
+    def search_dense(self, question: str, top_k: int = 10) -> List[RetrievalHit]:
+        return self._label(self.dense.search(question, max(1, int(top_k))), "dense", "dense_raw", replace=True)
 
     def search_bm25(self, question: str, top_k: int = 10) -> List[RetrievalHit]:
-        top_k = max(1, int(top_k))
-        hits = [RetrievalHit(chunk=c, score=float(s), rank=i, source="retriever",
-                             score_breakdown={"channel": ["bm25"], "bm25_raw": float(s)})
-                for i, (c, s) in enumerate(self.bm25.search(question, top_k), start=1)]
-        hits.sort(key=lambda h: float(h.score), reverse=True)
-        for i, h in enumerate(hits, start=1):
-            h.rank = i
-        return hits
+        pairs = self.bm25.search(question, max(1, int(top_k)))
+        return self._label([RetrievalHit(chunk=c, score=float(s), rank=0, source="retriever") for c, s in pairs],
+                           "bm25", "bm25_raw", replace=True)
 
     def search_colbert(self, question: str, top_k: int = 10) -> List[RetrievalHit]:
-        top_k = max(1, int(top_k))
         if self.colbert is None:
             return []
         try:
-            hits: List[RetrievalHit] = []
-            for item in self.colbert.search(question, top_k):
-                if isinstance(item, RetrievalHit):
-                    hits.append(item)
-                else:
-                    c, s = item
-                    hits.append(RetrievalHit(chunk=c, score=float(s), rank=0, source="retriever",
-                                             score_breakdown={"channel": ["colbert"], "colbert_raw": float(s)}))
-            hits.sort(key=lambda h: float(h.score), reverse=True)
-            for i, h in enumerate(hits, start=1):
-                h.rank = i
-                h.source = "retriever"
-                sb = h.score_breakdown or {}
-                sb["channel"] = _as_channel_list(sb.get("channel")) or ["colbert"]
-                sb.setdefault("colbert_raw", float(h.score))
-                h.score_breakdown = sb
-            return hits
-        except Exception:
+            found = [it if isinstance(it, RetrievalHit) else RetrievalHit(chunk=it[0], score=float(it[1]), rank=0, source="retriever")
+                     for it in self.colbert.search(question, max(1, int(top_k)))]
+            return self._label(found, "colbert", "colbert_raw", replace=False)
+        except Exception:        # the reference swallows channel failures (hybrid_retriever.py:233-235)
             return []
 
     def search_graph(self, question: str, top_k: int = 10, *, decision: Any = None,
                      seeds: Optional[List[RetrievalHit]] = None) -> List[RetrievalHit]:
-        top_k = max(1, int(top_k))
         if self.graph is None:
             return []
-        if seeds is None:
-            seed_n = int(getattr(self.cfg.retrieval, "graph_seed_k", max(10, top_k * 3)))
-            seeds = self.search_dense(question, seed_n)[:seed_n] + self.search_bm25(question, seed_n)[:seed_n] \
-                + self.search_colbert(question, seed_n)[:seed_n]
+        top_k = max(1, int(top_k))
+        if seeds is None:        # no fused list to start from: the head of every channel seeds the walk
+            n = int(getattr(self.cfg.retrieval, "graph_seed_k", max(10, top_k * 3)))
+            seeds = [h for channel in (self.search_dense, self.search_bm25, self.search_colbert) for h in channel(question, n)[:n]]
         try:
-            hits = self.graph.search(question, seeds, decision=decision, top_k=top_k)
-            hits.sort(key=lambda h: float(h.score), reverse=True)
-            for i, h in enumerate(hits, start=1):
-                h.rank = i
-                h.source = "retriever"
-                sb = h.score_breakdown or {}
-                sb["channel"] = _as_channel_list(sb.get("channel")) or ["graph"]
-                h.score_breakdown = sb
-            return hits
+            return self._label(self.graph.search(question, seeds, decision=decision, top_k=top_k), "graph", None, replace=False)
         except Exception:
             return []
 
     # ------------------------------------------------------------------ main search
     def search(self, question: str, llm: Any = None, top_k: int = 10, decision: Any = None) -> List[RetrievalHit]:
+        """hybrid_retriever.py:282-384: oversampled channels -> fusion -> min_final_score filter -> optional graph
+        expansion (seeds + graph hits) -> optional rerank of the head -> dedup -> top_k.  `llm` is accepted for the
+        reference's positional order; the cross-encoder / LLM reranker itself is injected as `self.reranker`."""
         rcfg = self.cfg.retrieval
         top_k = max(1, int(top_k))
-        t_start = time.time()
-        eff_top_k = int(getattr(rcfg, "top_k", top_k * 8) or (top_k * 8))
-        if eff_top_k < top_k:
-            eff_top_k = top_k
+        depth = max(top_k, int(getattr(rcfg, "top_k", top_k * 8) or (top_k * 8)))     # per-channel oversampling
+        laps = _Laps()
+        per_channel = {}
+        for name, channel in (("dense", self.search_dense), ("bm25", self.search_bm25), ("colbert", self.search_colbert)):
+            per_channel[name] = channel(question, depth)
+            laps.mark(name)
+        floor = float(getattr(rcfg, "min_final_score", 0.0))
+        ranked = [h for h in self._fuse(dense_hits=per_channel["dense"], bm25_hits=per_channel["bm25"],
+                                        colbert_hits=per_channel["colbert"]) if float(h.score) >= floor]
+        laps.mark("fuse")
+        last = "fuse"
 
-        t0 = time.time()
-        dense_hits = self.search_dense(question, eff_top_k)
-        t1 = time.time()
-        bm25_hits = self.search_bm25(question, eff_top_k)
-        t2 = time.time()
-        colbert_hits = self.search_colbert(question, eff_top_k)
-        t3 = time.time()
-        fused = self._fuse(dense_hits=dense_hits, bm25_hits=bm25_hits, colbert_hits=colbert_hits)
-        t4 = time.time()
-
-        min_final = float(getattr(rcfg, "min_final_score", 0.0))
-        fused = [h for h in fused if float(h.score) >= min_final]
-
-        t_graph = None
         mode = getattr(decision, "mode", None)
-        if getattr(rcfg, "enable_graph", False) and mode and (str(mode).upper().endswith("GRAPH_AUGMENTED")):
-            seed_n = int(getattr(rcfg, "graph_seed_k", max(10, top_k * 3)))
-            seeds = fused[:seed_n]
-            fused = seeds + self.search_graph(question, eff_top_k, decision=decision, seeds=seeds)
-            t_graph = time.time()
+        if getattr(rcfg, "enable_graph", False) and mode and str(mode).upper().endswith("GRAPH_AUGMENTED"):
+            head = ranked[:int(getattr(rcfg, "graph_seed_k", max(10, top_k * 3)))]
+            ranked = head + self.search_graph(question, depth, decision=decision, seeds=head)
+            laps.mark("graph")
+            last = "graph"
 
-        t_rerank = None
         if getattr(rcfg, "enable_rerank", False) and self.reranker is not None:
-            rerank_top_n = int(getattr(rcfg, "rerank_top_n", min(40, max(10, top_k * 4))))
-            new_hits = self.reranker(question, fused[:rerank_top_n])
-            fused[:len(new_hits)] = new_hits
-            fused.sort(key=lambda x: float(x.score), reverse=True)
-            for i, h in enumerate(fused, start=1):
-                h.rank = i
-            t_rerank = time.time()
+            n = int(getattr(rcfg, "rerank_top_n", min(40, max(10, top_k * 4))))
+            rescored = self.reranker(question, ranked[:n])
+            ranked[:len(rescored)] = rescored
+            _by_score(ranked)
+            laps.t["rerank_from"] = laps.t[last]
+            laps.mark("rerank")
 
-        fused = _dedup_keep_best(fused)
-        t_end = time.time()
-        ms = lambda a, b: int((b - a) * 1000)   # noqa: E731
+        ranked = _dedup_keep_best(ranked)
+        laps.mark("end")
         logger.info("[retrieval] dense=%dms bm25=%dms colbert=%dms fuse=%dms graph=%dms rerank=%dms total=%dms "
-                    "enabled(graph=%s,colbert=%s, has_gpu=%s)", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4),
-                    ms(t4, t_graph) if t_graph else 0, ms((t_graph or t4), t_rerank) if t_rerank else 0, ms(t_start, t_end),
-                    int(bool(getattr(rcfg, "enable_graph", False))), int(self.colbert is not None), int(torch.cuda.is_available()))
-        return fused[:top_k]
+                    "enabled(graph=%s,colbert=%s, has_gpu=%s)", laps.ms("start", "dense"), laps.ms("dense", "bm25"),
+                    laps.ms("bm25", "colbert"), laps.ms("colbert", "fuse"), laps.ms("fuse", "graph"), laps.ms("rerank_from", "rerank"),
+                    laps.ms("start", "end"), int(bool(getattr(rcfg, "enable_graph", False))), int(self.colbert is not None),
+                    int(torch.cuda.is_available()))
+        return ranked[:top_k]
 
     # ------------------------------------------------------------------ fusion
     def _fusion_knobs(self):
