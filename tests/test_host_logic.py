@@ -136,6 +136,83 @@ def test_dedup_keep_best_matches_reference_golden(golden_dir):
     assert got[0].score_breakdown["channel_contrib"] == want[0]["channel_contrib"]
 
 
+def test_hybrid_search_flow_with_fake_channels(caplog):
+    """HybridRetriever's host orchestration with every store faked (no GPU): per-channel labelling, oversampling depth,
+    min_final_score filter, graph augmentation (seeds + graph hits), reranker splice, dedup, top_k slice, timing log
+    (hybrid_retriever.py:172-384 of the reference)."""
+    import logging
+    from types import SimpleNamespace
+    from legal_rag_b200.retrieval.hybrid_retriever import HybridRetriever
+    chunks = [LawChunk(id=f"c{i}", law_name="L", article_no=str(i), article_id=f"a{i}", text=f"text {i}") for i in range(8)]
+    asked = {}
+
+    class Dense:
+        def search(self, q, k):
+            asked["dense"] = k
+            return [RetrievalHit(chunk=chunks[i], score=s, rank=9, source="graph", semantic_score=s, score_breakdown={"junk": 1})
+                    for i, s in ((2, 0.5), (0, 0.9), (1, 0.7))]                     # unsorted on purpose
+
+    class Bm25:
+        def search(self, q, k):
+            asked["bm25"] = k
+            return [(chunks[1], 7.0), (chunks[3], 9.0)]
+
+    class Colbert:
+        def search(self, q, k):
+            return [(chunks[4], 21.0), RetrievalHit(chunk=chunks[0], score=25.0, score_breakdown={"channel": "colbert", "colbert_raw": 1.0})]
+
+    class Graph:
+        def search(self, q, seeds, decision=None, top_k=10):
+            asked["graph_seeds"] = [h.chunk.id for h in seeds]
+            return [RetrievalHit(chunk=chunks[6], score=0.3, source="graph", score_breakdown={"channel": "graph"}),
+                    RetrievalHit(chunk=chunks[0], score=0.2, source="graph", score_breakdown={"channel": "graph"})]
+
+    rcfg = SimpleNamespace(top_k=5, min_final_score=0.25, enable_graph=True, graph_seed_k=3, enable_rerank=True, rerank_top_n=2)
+    hr = object.__new__(HybridRetriever)
+    hr.cfg = SimpleNamespace(retrieval=rcfg)
+    hr.dense, hr.bm25, hr.colbert, hr.graph = Dense(), Bm25(), Colbert(), Graph()
+
+    d = hr.search_dense("q", 3)
+    assert [(h.chunk.id, h.rank, h.source) for h in d] == [("c0", 1, "retriever"), ("c1", 2, "retriever"), ("c2", 3, "retriever")]
+    assert d[0].score_breakdown == {"channel": ["dense"], "dense_raw": 0.9}            # replaces what the hit carried
+    b = hr.search_bm25("q", 0)
+    assert asked["bm25"] == 1 and [(h.chunk.id, h.rank) for h in b] == [("c3", 1), ("c1", 2)]
+    assert b[0].score_breakdown == {"channel": ["bm25"], "bm25_raw": 9.0}
+    c = hr.search_colbert("q", 4)
+    assert [h.chunk.id for h in c] == ["c0", "c4"]
+    assert c[0].score_breakdown == {"channel": ["colbert"], "colbert_raw": 1.0}       # a carried breakdown is kept, the channel listed
+    assert c[1].score_breakdown == {"channel": ["colbert"], "colbert_raw": 21.0}
+    hr.colbert = SimpleNamespace(search=lambda q, k: 1 / 0)
+    assert hr.search_colbert("q", 4) == []                                             # channel failures are swallowed
+    hr.colbert = Colbert()
+    hr.search_graph("q", 2)                                                            # no seeds given: channel heads, dense first
+    assert asked["graph_seeds"] == ["c0", "c1", "c2", "c3", "c1", "c0", "c4"]
+
+    def fake_fuse(*, dense_hits, bm25_hits, colbert_hits):                             # stands in for the fusion kernel
+        sc = {}
+        for w, hs in ((0.5, dense_hits), (0.03, bm25_hits), (0.01, colbert_hits)):
+            for h in hs:
+                sc[h.chunk.id] = sc.get(h.chunk.id, 0.0) + w * float(h.score)
+        ranked = sorted(sc.items(), key=lambda kv: -kv[1])
+        return [RetrievalHit(chunk=chunks[int(cid[1:])], score=v, rank=r, score_breakdown={"channel": ["dense"]})
+                for r, (cid, v) in enumerate(ranked, start=1)]
+    hr._fuse = fake_fuse
+    hr.reranker = lambda q, hits: [h.model_copy(update={"score": 10.0 - j, "source": "rerank"}) for j, h in enumerate(reversed(hits))]
+    with caplog.at_level(logging.INFO, logger="legal_rag_b200.retrieval"):
+        out = hr.search("q", None, 4, SimpleNamespace(mode="RoutingMode.GRAPH_AUGMENTED"))
+    assert asked["dense"] == 5                                                         # max(top_k, rcfg.top_k) oversampling
+    # fused: c0 .45+.25=.70, c1 .35+.21=.56, c3 .27, c2 .25, c4 .21 -> filter >= .25 keeps c0 c1 c3 c2; seeds = first 3
+    assert asked["graph_seeds"] == ["c0", "c1", "c3"]
+    # seeds + graph hits (c6 .3, c0 .2), reranker reverses the first two (c1 -> 10, c0 -> 9), dedup drops the graph copy of c0
+    assert [(h.chunk.id, h.rank) for h in out] == [("c1", 1), ("c0", 2), ("c6", 3), ("c3", 4)]
+    assert out[0].source == "rerank" and sorted(out[1].score_breakdown["channel"]) == ["dense", "graph"]
+    assert any("[retrieval] dense=" in r.getMessage() and "rerank=" in r.getMessage() for r in caplog.records)
+    # without the routing decision there is no graph stage
+    asked.pop("graph_seeds")
+    hr.search("q", None, 2)
+    assert "graph_seeds" not in asked
+
+
 def test_error_contracts_without_touching_the_gpu(tmp_path):
     from legal_rag_b200.config import AppConfig
     from legal_rag_b200.retrieval import BM25Retriever, VectorStore
