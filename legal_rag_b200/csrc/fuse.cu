@@ -7,7 +7,8 @@
 //   load -> per-channel min/max (one fused reduction) -> id -> {position in each channel} through a
 //   shared-memory hash table (the reference's dict lookups; a linear search here made the pass
 //   quadratic in kc) -> RRF min/max -> score -> filter -> bitonic sort of packed 64-bit keys
-//   (ord32(score) << 32 | ~entry; equal scores fall back to comparing the int64 ids) -> top-k + breakdown.
+//   (ord32(score) << 32 | ~id when every id fits 32 bits: a plain integer compare; else | ~entry with an int64 id
+//   compare on equal scores) -> top-k + breakdown.
 // Arithmetic is fp64 like the reference's Python floats; only the stored scores are fp32.
 #include "common.cuh"
 
@@ -72,15 +73,19 @@ fuse_kernel(const FuseParams p) {
   for (int h = tid; h < H; h += FUSE_THREADS) { hkey[h] = ~0ull; hpos[3 * h] = hpos[3 * h + 1] = hpos[3 * h + 2] = FUSE_NONE; }
   __syncthreads();
   // ---- load; valid entries of a channel form a prefix (id == -1 padding at the tail) ----
+  bool wide_id = false;
   for (int e = tid; e < n3; e += FUSE_THREADS) {
     const int ch = e / kc, pos = e - ch * kc;
     int64_t id = -1; float s = 0.f;
     if (p.i[ch]) { id = p.i[ch][size_t(q) * kc + pos]; s = p.s[ch][size_t(q) * kc + pos]; }
     ids[e] = id; sc[e] = s;
+    wide_id |= id > int64_t(0xffffffffll);
     // the last valid entry of a channel is followed by padding (or by the end of the list): few threads reach the atomic
     if (id >= 0 && (pos == kc - 1 || p.i[ch][size_t(q) * kc + pos + 1] < 0)) atomicMax(&nvalid[ch], pos + 1);
   }
-  __syncthreads();
+  // Sort keys carry ~id in their low word when every id of the query fits 32 bits (the order (score desc, id asc) is then
+  // a plain integer compare); otherwise ~entry, with an id lookup on equal scores.
+  const bool wide = __syncthreads_or(wide_id);
   // ---- per-channel min / max (hybrid_retriever.py:24-30) and the id table, one pass ----
   float mm[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};     // fp32 inputs: their min / max are exact in fp32
   for (int e = tid; e < n3; e += FUSE_THREADS) {
@@ -143,7 +148,8 @@ fuse_kernel(const FuseParams p) {
     else if (p.method == 3) s = p.alpha * rn + (1.0 - p.alpha) * wsum[e];
     else s = rn;
     // rank on the value that is returned (fp32), so equal outputs are ordered by id
-    if (s >= p.min_final) skey[e] = ((unsigned long long)ord32(float(s) + 0.0f) << 32) | (unsigned long long)(0xffffffffu - uint32_t(e));   // + 0: no -0
+    if (s >= p.min_final)      // + 0.0f: no -0
+      skey[e] = ((unsigned long long)ord32(float(s) + 0.0f) << 32) | (unsigned long long)(0xffffffffu - (wide ? uint32_t(e) : uint32_t(ids[e])));
   }
   __syncthreads();
   // ---- bitonic sort by (score desc, id asc); dropped entries (key 0) sink ----
@@ -160,7 +166,8 @@ fuse_kernel(const FuseParams p) {
         const int l = 2 * i - (i & (stride - 1)), h = l + stride;
         const unsigned long long a = skey[l], b = skey[h];
         const bool desc = ((l & size) == 0);
-        if (desc ? before(b, a) : before(a, b)) { skey[l] = b; skey[h] = a; }
+        const bool swap = wide ? (desc ? before(b, a) : before(a, b)) : (desc ? b > a : a > b);
+        if (swap) { skey[l] = b; skey[h] = a; }
       }
       const int next = stride > 1 ? stride >> 1 : size;       // stride of the step that follows (size = 2 * size / 2)
       if (stride > 32 || next > 32) __syncthreads(); else __syncwarp();
@@ -178,12 +185,14 @@ fuse_kernel(const FuseParams p) {
       if (bd) for (int j = 0; j < 8; ++j) bd[j] = 0.f;
       continue;
     }
-    const int e = int(0xffffffffu - uint32_t(key));
-    const int64_t id = ids[e];
+    int e = int(0xffffffffu - uint32_t(key));                   // wide ids: the entry; else the id itself
+    const int64_t id = wide ? ids[e] : int64_t(0xffffffffu - uint32_t(key));
     *os = unord32(uint32_t(key >> 32)); *oi = id;
     if (!bd) continue;
     uint32_t h = fuse_hash(id, H);
     while (hkey[h] != (unsigned long long)id) h = (h + 1) & uint32_t(H - 1);
+    if (!wide)                                                  // the owning entry: first occurrence in the first channel that lists the id
+      e = hpos[3 * h] != FUSE_NONE ? hpos[3 * h] : (hpos[3 * h + 1] != FUSE_NONE ? kc + hpos[3 * h + 1] : 2 * kc + hpos[3 * h + 2]);
     double norm[3] = {0, 0, 0}, raw[3] = {0, 0, 0};
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
