@@ -13,7 +13,8 @@ from pathlib import Path
 
 import torch  # noqa: F401  (loads libcudart before liblrag)
 
-LIB_PATH = Path(__file__).resolve().parent / "liblrag.so"
+# LRAG_LIB_PATH: an alternative build of the same library (A/B runs of kernel variants); never a different implementation
+LIB_PATH = Path(os.environ.get("LRAG_LIB_PATH") or Path(__file__).resolve().parent / "liblrag.so")
 
 LRAG_MAX_K = 1024
 LRAG_BM25_MAX_QUERY_TERMS = 128

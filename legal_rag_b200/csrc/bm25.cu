@@ -3,10 +3,12 @@
 // of the reference; rank_bm25.BM25Okapi semantics, see oracle/bm25.py).
 //
 // Integer/float streaming work over posting lists, no tensor cores; HBM sees every posting range once,
-// the rest is served from L2, so the binding resource is the SM side (issue slots, shared memory).
+// the rest is served from L2, so the binding resource is the SM side: load/store-unit cycles (one
+// global load pair + one shared-memory atomic per posting) and issue slots.
 //
 // Work decomposition.  A *chain* is one (query, doc split) pair; it walks its split in *items* of
-// `item_slabs` slabs (BM25_SLAB docs = 48 KB of int32 fixed-point accumulators in shared memory).  Items are
+// `item_slabs` slabs (a slab = `slab` docs of int32 fixed-point accumulators in shared memory, as many
+// as two resident CTAs per SM allow: 22 528 docs = 88 KB for k <= 256).  Items are
 // numbered step-major -- item = step * n_chains + chain -- and handed out by an atomic counter to
 // persistent CTAs, so at any moment the whole machine works on the same narrow doc range of every
 // query: a posting list is fetched from HBM once per range and then served from L2 to all the other
@@ -14,30 +16,36 @@
 // threshold, surviving candidates) lives in the workspace; item (step, chain) waits on a flag that
 // item (step - 1, chain) -- always a lower item number, so already claimed by a running CTA -- sets.
 //
-// The CTA is warp-specialised so that posting traffic never waits for the arithmetic and the
-// arithmetic never does bookkeeping:
+// The CTA is warp-specialised so that the arithmetic never does bookkeeping:
 //   * bounds warp   -- claims the next item, loads the chain's term cursors and finds the posting
 //                      boundaries of every query term at every slab edge with one parallel round of
 //                      windowed binary searches (postings are doc-id sorted); double-buffered, one
-//                      group of slabs ahead of the copy warps;
-//   * 3 copy warps  -- walk the (slab, term) runs in order (the lanes look up one term each) and stream
-//                      them, <= BM25_CHUNK postings at a time, into a shared-memory ring with bulk async
-//                      copies (cp.async.bulk, 16-byte aligned source windows) that complete on mbarriers;
-//                      chunk c is issued by warp c mod 3.  The short runs of a slab (rare terms) are
-//                      packed into ONE stage with 4-byte cp.async copies.  Each ring stage carries a
-//                      descriptor {count, skip, term multiplicity x scale, slab base, flags}: the
-//                      consumers are a plain interpreter of that stream;
-//   * 16 consumer warps -- per stage add `mult * impact` into acc[doc - slab0] with one shared-memory
-//                      integer atomic per posting: scores are kept in fixed point (int32, a per-query
-//                      power-of-two scale sized from `impact_bound`), so adds commute exactly, the
-//                      terms of a slab need no barrier between them and the result is independent
-//                      of scheduling.  Each thread keeps a running max of what it wrote.  At
-//                      SLAB_END one `bar.red.or` tells whether any thread wrote a score that reaches
-//                      the query's running k-th best: only then is the slab scanned for candidates
+//                      group of slabs ahead of the emit warp;
+//   * emit warp     -- turns the (slab, term) runs into *segment descriptors* {first posting, count <=
+//                      BM25_SEG, term multiplicity x scale} in a shared-memory descriptor ring (the lanes
+//                      write the segments of a slab in parallel), and keeps a small ring of *epoch
+//                      records*: an epoch is one slab visit (or an item's begin / end control point);
+//                      a record says where the epoch's descriptors end;
+//   * 16 consumer warps -- each claims the next descriptor (one shared-memory atomic per warp), loads the
+//                      segment's (doc, impact) pairs straight from global memory / L2 into registers
+//                      (coalesced 4-byte loads, L1 no-allocate: no shared-memory staging, no per-stage
+//                      hand-shake between warps) and adds `mult * impact` into acc[doc - slab0] with one
+//                      shared-memory integer atomic per posting: scores are kept in fixed point (int32, a
+//                      per-query power-of-two scale sized from `impact_bound`), so adds commute exactly, the
+//                      segments of a slab need no ordering between them and the result is independent
+//                      of scheduling.  Each thread keeps a running max of what it wrote.  A warp whose
+//                      claimed descriptor lies past the end of the current epoch goes to the epoch's end:
+//                      one `bar.red.or` tells whether any thread wrote a score that reaches
+//                      the query's running k-th best; only then is the slab scanned for candidates
 //                      (appended to a shared buffer; an overflow triggers an exact radix select that
-//                      raises the threshold).  The slab is re-zeroed.
-//                      ITEM_BEGIN / ITEM_END stages load / store the chain's candidate state; the
+//                      raises the threshold).  The slab is re-zeroed.  The loads of the next epoch's first
+//                      segment are already in flight while the warp sits in those barriers.
+//                      Item-begin / item-end epochs load / store the chain's candidate state; the
 //                      chain's last item sorts its top-k into the per-chain key list.
+// Round 1 staged postings through a bulk-copy ring that all 16 warps consumed stage by stage: 44 warp
+// instructions and 10 shared-memory wavefronts per 32 postings (ring write + ring read + atomic + the
+// per-stage hand-shake).  The direct loads need ~12 instructions and ~6 load/store-unit cycles
+// (tools/micro/bm25_stream.cu: 1.2-1.5 T postings/s against 0.44-0.71 T for the ring).
 // Slabs in which no query term has a posting are skipped when impacts are known non-negative;
 // documents that match nothing (score 0) are then added by the merge step, lowest id first, exactly
 // as the reference's stable sort does.  bm25_merge_kernel merges the per-split lists of a query.
@@ -51,23 +59,30 @@
 namespace lrag {
 
 constexpr int BM25_CONSUMERS = 512;                  // 16 warps
-constexpr int BM25_COPY_WARPS = 3;                   // chunk c is issued by copy warp c % BM25_COPY_WARPS; must not exceed BM25_STAGES (phase parity)
-constexpr int BM25_THREADS = BM25_CONSUMERS + 32 * BM25_COPY_WARPS + 32;   // consumers, copy warps, bounds warp
-constexpr int BM25_SLAB = 12288;
+constexpr int BM25_THREADS = BM25_CONSUMERS + 64;    // consumers, emit warp, bounds warp
+constexpr int BM25_SLAB_STEP = 4 * BM25_CONSUMERS;   // slab sizes are multiples of one int4 per consumer thread
+constexpr int BM25_SLAB_MAX = 12 * BM25_SLAB_STEP;   // 24 576 docs = 96 KB
 constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (fewer when a query has many terms)
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
 constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
-constexpr int BM25_CHUNK = 2048;                     // postings per ring stage
-constexpr int BM25_STAGES = 3;                       // 48 KB slab + 48 KB ring + 4 KB candidates + 11 KB state: two CTAs per SM
-constexpr int BM25_RING_BYTES = BM25_STAGES * BM25_CHUNK * 8;
+#ifndef LRAG_BM25_SEG
+#define LRAG_BM25_SEG 256
+#endif
+#ifndef LRAG_BM25_CLAIM_AHEAD
+#define LRAG_BM25_CLAIM_AHEAD 1
+#endif
+#ifndef LRAG_BM25_HOTLIST
+#define LRAG_BM25_HOTLIST 1
+#endif
+constexpr int BM25_SEG = LRAG_BM25_SEG;              // postings per segment descriptor (8 per lane)
+constexpr int BM25_SEG_PER_LANE = BM25_SEG / 32;
+constexpr int BM25_RING = 128;                       // segment descriptors in flight
+constexpr int BM25_EPOCHS = 16;                      // epoch records in flight
+constexpr int BM25_HOT = 512;                        // docs per slab whose running score reached the threshold (more: full scan)
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
-constexpr int BM25_PER_THREAD = BM25_CHUNK / BM25_CONSUMERS;
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
-static_assert(BM25_COPY_WARPS <= BM25_STAGES, "a copy warp may run at most one ring phase ahead of the consumers");
-constexpr int BM25_DEFAULT_ITEM_SLABS = 32;
-constexpr int BM25_GATHER_MAX = 64;                  // runs this short share one ring stage (32 runs x 64 postings fill it at most)
-static_assert(32 * BM25_GATHER_MAX <= BM25_CHUNK, "a gather stage must hold one lane batch of short runs");
-enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
+constexpr int BM25_DEFAULT_ITEM_DOCS = 32 * 12288;   // docs per work item (the item is a whole number of slabs)
+enum : int { BM25_E_SLAB = 1, BM25_E_ITEM_BEGIN = 2, BM25_E_ITEM_END = 4, BM25_E_FINAL = 8, BM25_E_END = 16 };
 
 struct Bm25Ws {
   unsigned long long* counter;     // next item
@@ -91,11 +106,12 @@ struct Bm25Params {
   int64_t N; int64_t dps;          // docs per split (multiple of the item size)
   unsigned long long total_items;
   int nq, k, nonneg, S, cap, P, TS, item_slabs, steps, nc;
+  int slab;                        // docs per slab (multiple of BM25_SLAB_STEP)
   float impact_bound;              // >= max |impact| over the index
   Bm25Ws ws;
 };
 
-struct Bm25Group {                 // bounds warp -> copy warp
+struct Bm25Group {                 // bounds warp -> emit warp
   int kind;                        // 0 = slabs of an item, 1 = no more work
   int chain, step, first, last, final_step, nt, ns;
   int b0, range_end;
@@ -106,10 +122,26 @@ struct Bm25Group {                 // bounds warp -> copy warp
   int32_t last_t[BM25_MAX_GROUP];  // last term with postings in the slab, -1 = none
 };
 
+// One epoch = one slab visit or one control point of an item.  Written by the emit warp: the fields, then
+// `pub` = epoch + 1; after the epoch's last descriptor `end_idx` (index of the first descriptor of any later
+// epoch), then `closed` = epoch + 1.  The slot of epoch e is reused for e + BM25_EPOCHS once the consumers
+// have set `epochs_done` past e.
+struct Bm25Epoch {
+  int slab0, flags, chain, step;
+  float inv_scale;
+  int end_idx;
+  int pub, closed;
+};
+
 struct Bm25Shared {
   SelectShared sel;
-  int4 sdesc[BM25_STAGES];         // {n | skip << 12 | flags << 16, mult x scale (float bits) or step, slab0 or chain, 1/scale bits}
-  uint64_t full_bar[BM25_STAGES], empty_bar[BM25_STAGES];   // posting ring
+  int4 ring[BM25_RING];            // {base lo | lo slot, base hi(16) | (hi slot - 1) << 16 | (epoch & 255) << 24, mult x scale bits, lap + 1}
+  int hot[BM25_HOT];               // docs of the current slab whose running score reached the threshold
+  int hot_cnt;
+  int freelap[BM25_RING];          // lap for which the slot may be written next
+  Bm25Epoch epoch[BM25_EPOCHS];
+  int head;                        // next descriptor index to claim
+  int epochs_done;                 // epochs the consumers have left behind
   uint64_t bfull_bar[2], bempty_bar[2];                      // group buffers
   Bm25Group grp[2];
   int64_t t_start[BM25_MAXT];      // bounds warp's view of the current item's query
@@ -117,7 +149,10 @@ struct Bm25Shared {
   int32_t t_cur[BM25_MAXT];
   int cand_cnt;
   unsigned long long thr_key;
+  float inv_scale;                 // fixed point -> fp32 score of the current item's query
+  int range_end;                   // docs at or past the end of the chain's split are not ranked
 };
+constexpr int BM25_SH_BYTES = (int(sizeof(Bm25Shared)) + 127) / 128 * 128;   // the slab follows the control block
 
 __device__ __forceinline__ int lower_bound_doc(const int32_t* __restrict__ ids, int lo, int hi, int64_t target) {
   // first index in [lo, hi) whose doc id >= target
@@ -128,13 +163,49 @@ __device__ __forceinline__ int lower_bound_doc(const int32_t* __restrict__ ids, 
   return lo;
 }
 
-// 4-byte asynchronous global -> shared copy of the executing thread, and the arrive that fires on an
-// mbarrier once all of this thread's earlier copies have landed (pending count +1 now, -1 then)
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+// streaming 4-byte loads of postings: read-only path, no L1 allocation (every posting is used once per CTA)
+__device__ __forceinline__ int ldg_stream_s32(const int32_t* p) {
+  int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
-__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+}
+// shared-memory words that another warp of the CTA publishes
+__device__ __forceinline__ int lds_volatile(const int* p) {
+  int v; asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory"); return v;
+}
+__device__ __forceinline__ void sts_volatile(int* p, int v) {
+  asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// Bounded spin on a shared-memory word until it equals / reaches a value.
+__device__ __forceinline__ void spin_shared(const int* p, int want, bool at_least) {
+  int v = lds_volatile(p);
+  if (at_least ? v >= want : v == want) return;
+  const long long t0 = clock64();
+  for (;;) {
+    __nanosleep(32);
+    v = lds_volatile(p);
+    if (at_least ? v >= want : v == want) return;
+    if (clock64() - t0 > 20000000000LL) {
+      printf("lrag: bm25 shared-memory wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// mbarrier wait of the two bookkeeping warps: they wait long and often, so they sleep between polls and leave the
+// issue slots to the consumers
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_now(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+    __nanosleep(128);
+    if (mbar_try_wait_now(bar, parity)) return;
+    if (clock64() - t0 > 20000000000LL) {
+      printf("lrag: bm25 group-buffer wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
 }
 
 // barrier over the consumer warps that also ORs a predicate across them
@@ -197,10 +268,10 @@ __device__ __forceinline__ void cand_append(bool want, uint64_t key, uint64_t* c
 
 struct Bm25Union {
   const uint64_t* cand; int ncand;
-  const int* acc; float inv_scale; int64_t slab0; int64_t range_end; unsigned long long thr_key;
+  const int* acc; float inv_scale; int64_t slab0; int64_t range_end; unsigned long long thr_key; int slab;
   template <class F> __device__ void operator()(F&& f) const {
     for (int i = threadIdx.x; i < ncand; i += BM25_CONSUMERS) f(cand[i]);
-    for (int i = threadIdx.x; i < BM25_SLAB; i += BM25_CONSUMERS) {
+    for (int i = threadIdx.x; i < slab; i += BM25_CONSUMERS) {
       const int64_t doc = slab0 + i;
       if (doc >= range_end) break;
       const uint64_t key = make_key(float(acc[i]) * inv_scale, uint32_t(doc));
@@ -264,35 +335,229 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epoch changes of the consumer warps.  Kept out of line: the segment loop holds sixteen loaded postings in
+// registers while a warp changes epochs, and this code (barriers, candidate selection, chain state) must not
+// take part in that loop's register allocation.
+// ------------------------------------------------------------------------------------------------
+struct Bm25Slab { uint32_t accb; int thr_i; int end; };      // what the segment loop needs from an epoch
+
+// Leaves epoch `e`: ranks the slab's hot docs (or the whole slab), re-zeroes it, stores the chain state at an item's end.
+__device__ __noinline__ void bm25_end_epoch(const Bm25Params& p, Bm25Shared& sh, int e) {
+  const int tid = threadIdx.x;
+  const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
+  const int SLAB = p.slab, cap = p.cap;
+  int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(acci + SLAB);
+  const Bm25Epoch& r = sh.epoch[e & (BM25_EPOCHS - 1)];
+  const int ep_flags = r.flags, ep_chain = r.chain, ep_step = r.step;
+  const int64_t slab0 = r.slab0;
+  const float inv_scale = sh.inv_scale;
+  const int64_t range_end = sh.range_end;
+  bool synced = false;
+  if (ep_flags & BM25_E_SLAB) {
+    cbar();                                                 // every add of the slab is done
+    const int cnt_before = sh.cand_cnt;
+    const unsigned long long thr_key = sh.thr_key;
+    const int nh = sh.hot_cnt;
+    // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
+    const float thr_s = !thr_key ? -INFINITY
+                        : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+    // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s
+    int thr_i = INT_MIN;
+    if (thr_s > -INFINITY) {
+      const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
+      thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
+      if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
+    }
+    if (LRAG_BM25_HOTLIST && p.nonneg && nh <= BM25_HOT && cnt_before + nh <= cap) {
+      if (nh > 0) {
+        // ---- the hot docs: final score -> candidate (a doc noted twice is taken once: the read clears it) ----
+        for (int i0 = 0; i0 < nh; i0 += BM25_CONSUMERS) {
+          const int i = i0 + tid;
+          bool want = false;
+          uint64_t key = 0;
+          if (i < nh) {
+            const int doc = sh.hot[i];
+            const int val = atomicExch(acci + (doc - int(slab0)), 0);
+            const float sc = float(val) * inv_scale;
+            want = val >= thr_i && sc >= thr_s && int64_t(doc) < range_end;
+            if (want) { key = make_key(sc, uint32_t(doc)); want = key > thr_key; }
+          }
+          if (i0 + (tid & ~31) < nh) cand_append(want, key, cand, cap, &sh.cand_cnt);
+        }
+        cbar();                                             // hot docs are read before the slab is cleared
+      }
+    } else {
+      // ---- scan the slab for candidates ----
+      const int4* a4 = reinterpret_cast<const int4*>(acci);
+#pragma unroll 2
+      for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) {
+        const int idx = (tid + i * BM25_CONSUMERS) * 4;
+        const int4 s4 = a4[tid + i * BM25_CONSUMERS];
+        const bool any4 = max(max(s4.x, s4.y), max(s4.z, s4.w)) >= thr_i;
+        if (!__any_sync(0xffffffffu, any4)) continue;
+        const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
+#pragma unroll
+        for (int el = 0; el < 4; ++el) {
+          const int64_t doc = slab0 + idx + el;
+          bool want = (sv[el] >= thr_s) && (doc < range_end);
+          uint64_t key = 0;
+          if (want) { key = make_key(sv[el], uint32_t(doc)); want = key > thr_key; }
+          cand_append(want, key, cand, cap, &sh.cand_cnt);
+        }
+      }
+      cbar();
+      if (sh.cand_cnt > cap) {
+        // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
+        Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key, SLAB};
+        const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
+        uint64_t keep[BM25_KEEP];     // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
+#pragma unroll
+        for (int i = 0; i < BM25_KEEP; ++i) {
+          const int idx = tid + i * BM25_CONSUMERS;
+          keep[i] = idx < cnt_before ? cand[idx] : 0ull;
+        }
+        cbar();
+        if (tid == 0) sh.cand_cnt = 0;
+        cbar();
+#pragma unroll
+        for (int i = 0; i < BM25_KEEP; ++i) {
+          const bool want = keep[i] != 0ull && keep[i] >= pivot;
+          cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
+        }
+        for (int i = tid; i < SLAB; i += BM25_CONSUMERS) {
+          const int64_t doc = slab0 + i;
+          uint64_t key = 0;
+          bool want = doc < range_end;
+          if (want) { key = make_key(float(acci[i]) * inv_scale, uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
+          cand_append(want, key, cand, cap, &sh.cand_cnt);
+        }
+        cbar();
+        if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
+        cbar();
+      }
+    }
+    // ---- re-zero the slab for the next one ----
+    float4* z4 = reinterpret_cast<float4*>(acci);
+#pragma unroll 4
+    for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) sh.hot_cnt = 0;
+    cbar();
+    synced = true;
+  }
+  if (ep_flags & BM25_E_ITEM_END) {
+    const int chain = ep_chain, step = ep_step;
+    if (ep_flags & BM25_E_FINAL) {
+      // ---- sorted top-k of the surviving candidates -> this chain's key list ----
+      const int ncand = min(sh.cand_cnt, cap);
+      Bm25Cands cands{cand, ncand};
+      const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
+      uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acci);     // the (zeroed) slab doubles as the sort buffer
+      const int P = p.P;
+      if (tid == 0) sh.sel.nsel = 0;
+      cbar();
+      for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
+        const uint64_t key = cand[i];
+        if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
+      }
+      cbar();
+      block_sort_desc(sortbuf, P, cbar);
+      uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
+      for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
+      cbar();
+      for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
+      cbar();
+    } else {
+      const int cnt = min(sh.cand_cnt, cap);
+      uint64_t* dst = p.ws.ch_cand + size_t(chain) * cap;
+      for (int i = tid; i < cnt; i += BM25_CONSUMERS) dst[i] = cand[i];
+      if (tid == 0) { p.ws.ch_cnt[chain] = cnt; p.ws.ch_thr[chain] = sh.thr_key; }
+      __threadfence();
+      cbar();
+      if (tid == 0) st_release(p.ws.cand_flag + chain, step + 1);
+    }
+    synced = true;
+  }
+  if (!synced) cbar();      // every thread has stopped reading this epoch's record
+  if (tid == 0) sts_volatile(&sh.epochs_done, e + 1);
+}
+
+// Enters epoch `e`: loads the chain state at an item's begin; returns the slab's accumulator base and the fixed-point
+// threshold above which an add notes its doc (INT_MAX: never), and whether this is the END epoch.
+__device__ __noinline__ Bm25Slab bm25_begin_epoch(const Bm25Params& p, Bm25Shared& sh, int e) {
+  const int tid = threadIdx.x;
+  const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
+  const int cap = p.cap;
+  int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(acci + p.slab);
+  const Bm25Epoch& r = sh.epoch[e & (BM25_EPOCHS - 1)];
+  if ((tid & 31) == 0) spin_shared(&r.pub, e + 1, false);
+  __syncwarp();
+  __threadfence_block();
+  const int ep_flags = r.flags;
+  Bm25Slab out;
+  out.accb = smem_u32(acci) - 4u * uint32_t(r.slab0);      // accb + 4 * doc == &acc[doc - slab0]
+  out.thr_i = INT_MAX;
+  out.end = (ep_flags & BM25_E_END) ? 1 : 0;
+  if (out.end) return out;
+  if (ep_flags & BM25_E_ITEM_BEGIN) {
+    // the previous item ended behind a barrier: the candidate buffer is free
+    const int chain = r.chain, step = r.step;
+    const unsigned long long thr_init = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull;
+    if (tid == 0) {
+      sh.inv_scale = r.inv_scale;
+      sh.range_end = int(min(p.N, int64_t(chain % p.S + 1) * p.dps));
+    }
+    if (step == 0) {
+      if (tid == 0) { sh.cand_cnt = 0; sh.thr_key = thr_init; }
+    } else {
+      spin_until_ge(p.ws.cand_flag + chain, step);
+      const int cnt = __ldcg(p.ws.ch_cnt + chain);
+      const uint64_t* src = p.ws.ch_cand + size_t(chain) * cap;
+      for (int i = tid; i < cnt; i += BM25_CONSUMERS) cand[i] = __ldcg(src + i);
+      if (tid == 0) { sh.cand_cnt = cnt; sh.thr_key = __ldcg(p.ws.ch_thr + chain); }
+    }
+    cbar();
+  }
+  if ((ep_flags & BM25_E_SLAB) && LRAG_BM25_HOTLIST && p.nonneg) {
+    // the k-th best key was last changed behind a barrier
+    const unsigned long long thr_key = sh.thr_key;
+    const float thr_s = (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+    const float t = thr_s / sh.inv_scale;
+    int thr_i = t >= 2147483520.f ? INT_MAX : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1;
+    out.thr_i = thr_i < 1 ? 1 : thr_i;
+  }
+  return out;
+}
+
 __global__ void __launch_bounds__(BM25_THREADS, 2)
-bm25_scan_kernel(const Bm25Params p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* acc = reinterpret_cast<float*>(smem_raw);                                          // [BM25_SLAB]
-  int32_t* ring_id = reinterpret_cast<int32_t*>(smem_raw + BM25_SLAB * 4);                  // [STAGES][CHUNK]
-  float* ring_imp = reinterpret_cast<float*>(smem_raw + BM25_SLAB * 4 + BM25_RING_BYTES / 2);
-  uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw + BM25_SLAB * 4 + BM25_RING_BYTES); // [cap]
-  Bm25Shared& sh = *reinterpret_cast<Bm25Shared*>(smem_raw + BM25_SLAB * 4 + BM25_RING_BYTES + size_t(p.cap) * 8);
+bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int SLAB = p.slab;
+  Bm25Shared& sh = *reinterpret_cast<Bm25Shared*>(smem_raw);                                // control block first: constant addresses
+  float* acc = reinterpret_cast<float*>(smem_raw + BM25_SH_BYTES);                          // [SLAB], then the candidate keys [cap]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int cap = p.cap;
-  const unsigned long long thr_init = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull;
 
   if (tid == 0) {
     sh.cand_cnt = 0;
-    sh.thr_key = thr_init;
-    for (int s = 0; s < BM25_STAGES; ++s) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], BM25_CONSUMERS / 32); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], BM25_COPY_WARPS); }
+    sh.thr_key = 0ull;
+    sh.head = 0;
+    sh.epochs_done = 0;
+    sh.hot_cnt = 0;
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], 1); }
     fence_barrier_init();
   }
+  for (int i = tid; i < BM25_RING; i += BM25_THREADS) { sh.ring[i] = make_int4(0, 0, 0, 0); sh.freelap[i] = 0; }
+  for (int i = tid; i < BM25_EPOCHS; i += BM25_THREADS) { sh.epoch[i].pub = 0; sh.epoch[i].closed = 0; }
   // zero the slab once; every slab end leaves it zeroed again
-  for (int i = tid; i < BM25_SLAB / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < SLAB / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
-
-  if (warp == BM25_CONSUMERS / 32 + BM25_COPY_WARPS) {
+  if (warp == BM25_CONSUMERS / 32 + 1) {
     // ===================== bounds warp =====================
-    const int64_t item_docs = int64_t(p.item_slabs) * BM25_SLAB;
+    const int64_t item_docs = int64_t(p.item_slabs) * SLAB;
     uint32_t gcount = 0;
     for (;;) {
       unsigned long long item = 0;
@@ -322,14 +587,14 @@ bm25_scan_kernel(const Bm25Params p) {
       __syncwarp();
       int gs = nt > 0 ? BM25_BOUND_CAP / nt - 1 : BM25_MAX_GROUP;
       gs = gs < 1 ? 1 : (gs > BM25_MAX_GROUP ? BM25_MAX_GROUP : gs);
-      const int nslab = rb < re ? int((re - rb + BM25_SLAB - 1) / BM25_SLAB) : 0;
+      const int nslab = rb < re ? int((re - rb + SLAB - 1) / SLAB) : 0;
       const int ngroups = nslab > 0 ? (nslab + gs - 1) / gs : 1;
       for (int gi = 0; gi < ngroups; ++gi, ++gcount) {
         const uint32_t bb = gcount & 1;
-        mbar_wait(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
+        mbar_wait_lazy(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
         Bm25Group& G = sh.grp[bb];
         const int ns = max(0, min(gs, nslab - gi * gs));
-        const int64_t b0 = rb + int64_t(gi) * gs * BM25_SLAB;
+        const int64_t b0 = rb + int64_t(gi) * gs * SLAB;
         if (lane == 0) {
           G.kind = 0; G.chain = chain; G.step = step; G.first = (gi == 0); G.last = (gi == ngroups - 1);
           G.final_step = (step == p.steps - 1); G.nt = nt; G.ns = ns; G.b0 = int(b0); G.range_end = int(re);
@@ -343,7 +608,7 @@ bm25_scan_kernel(const Bm25Params p) {
           for (int w = lane; w < nt * (ns + 1); w += 32) {
             const int t = w / (ns + 1), j = w % (ns + 1);
             const int cur = sh.t_cur[t], len = sh.t_len[t];
-            int64_t target = b0 + int64_t(j) * BM25_SLAB;
+            int64_t target = b0 + int64_t(j) * SLAB;
             if (target > re) target = re;
             // ids are strictly increasing inside a term: the answer is at most (target - b0) past cur
             const int64_t reach = int64_t(cur) + (target - b0);
@@ -371,341 +636,214 @@ bm25_scan_kernel(const Bm25Params p) {
       __syncwarp();
     }
     const uint32_t bb = gcount & 1;
-    mbar_wait(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
+    mbar_wait_lazy(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
     if (lane == 0) { sh.grp[bb].kind = 1; mbar_arrive(&sh.bfull_bar[bb]); }
-  } else if (warp >= BM25_CONSUMERS / 32) {
-    // ===================== copy warps: postings -> shared-memory ring =====================
-    // Every copy warp walks the same chunk sequence and issues the chunks of its own residue class.
-    // Per slab the lanes look up one term's run each; the runs are then issued in term order, one
-    // short serial sequence per chunk (wait for a free stage, descriptor, expect_tx, two bulk copies).
-    uint32_t ps = 0, pph = 1;
-    int turn = warp - BM25_CONSUMERS / 32;      // chunks until this warp's next one
-    // returns the stage of the next chunk, or -1 when the chunk belongs to another copy warp
-    auto stage_acquire = [&]() {
-      const uint32_t s = ps;
-      const uint32_t ph = pph;
-      if (++ps == BM25_STAGES) { ps = 0; pph ^= 1; }
-      if (turn != 0) { --turn; return -1; }
-      turn = BM25_COPY_WARPS - 1;
-      mbar_wait(&sh.empty_bar[s], ph);
-      return int(s);
-    };
-    // control stage: no postings, just flags and two words for the consumers
-    auto emit_ctrl = [&](int flags, int y, int z, float w) {
-      const int s = stage_acquire();
-      if (s < 0) return;
+  } else if (warp == BM25_CONSUMERS / 32) {
+    // ===================== emit warp: (slab, term) runs -> segment descriptors + epoch records =====================
+    int epoch = 0;          // next epoch to open
+    int widx = 0;           // next descriptor index
+    auto open_epoch = [&](int slab0, int flags, int chain, int step, float inv_scale) {
       if (lane == 0) {
-        sh.sdesc[s] = make_int4(flags << 16, y, z, __float_as_int(w));
-        mbar_arrive(&sh.full_bar[s]);
+        // the slot still belongs to epoch - BM25_EPOCHS until the consumers have left that epoch behind
+        spin_shared(&sh.epochs_done, epoch - BM25_EPOCHS + 1, true);
+        Bm25Epoch& r = sh.epoch[epoch & (BM25_EPOCHS - 1)];
+        r.slab0 = slab0; r.flags = flags; r.chain = chain; r.step = step; r.inv_scale = inv_scale;
+        __threadfence_block();
+        sts_volatile(&r.pub, epoch + 1);
       }
       __syncwarp();
     };
-    // postings [first, first + n) -> one stage.  The copy window is widened to 16-byte units; the
-    // consumers ignore what lies outside [skip, skip + n).
-    auto emit = [&](int64_t first, int n, float mult, int sl0, int flags) {
-      const int s = stage_acquire();
-      if (s < 0) return;
-      const int skip = int(first & 3);
-      const int64_t a0 = first - skip;
-      int cnt4 = (n + skip + 3) & ~3;
-      int32_t* dst_id = ring_id + s * BM25_CHUNK;
-      float* dst_imp = ring_imp + s * BM25_CHUNK;
-      if (a0 + cnt4 > p.nnz) {
-        // the arrays end inside the last unit: those (at most 3) postings are moved by hand
-        cnt4 -= 4;
-        const int tail = int(p.nnz - (a0 + cnt4));
-        if (lane < tail) {
-          dst_id[cnt4 + lane] = __ldg(p.doc_id + a0 + cnt4 + lane);
-          dst_imp[cnt4 + lane] = __ldg(p.impact + a0 + cnt4 + lane);
-        }
-        __syncwarp();
-      }
-      if (lane == 0) {
-        sh.sdesc[s] = make_int4(n | (skip << 12) | (flags << 16), __float_as_int(mult), sl0, 0);
-        mbar_arrive_expect_tx(&sh.full_bar[s], uint32_t(cnt4) * 8u);
-        if (cnt4 > 0) {
-          bulk_copy_g2s(dst_id, p.doc_id + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
-          bulk_copy_g2s(dst_imp, p.impact + a0, uint32_t(cnt4) * 4u, &sh.full_bar[s]);
-        }
-      }
-      __syncwarp();
-    };
-    // Short runs (rare terms: a handful of postings per slab) with the same multiplier share ONE
-    // stage: the lanes copy each run with 4-byte asynchronous copies packed back to back,
-    // and the stage's barrier completes when every lane's copies have landed.
-    auto emit_gather = [&](uint32_t runs, int64_t first, int cnt, float mult, int sl0, int flags) {
-      const int s = stage_acquire();
-      if (s < 0) return;
-      int32_t* dst_id = ring_id + s * BM25_CHUNK;
-      float* dst_imp = ring_imp + s * BM25_CHUNK;
-      int total = 0;
-      while (runs) {
-        const int src = __ffs(runs) - 1;
-        runs &= runs - 1;
-        const int64_t f = __shfl_sync(0xffffffffu, first, src);
-        const int c = __shfl_sync(0xffffffffu, cnt, src);
-        for (int l = lane; l < c; l += 32) {
-          cp_async_4(dst_id + total + l, p.doc_id + f + l);
-          cp_async_4(dst_imp + total + l, p.impact + f + l);
-        }
-        total += c;
-      }
-      cp_async_mbar_arrive(&sh.full_bar[s]);
+    auto close_epoch = [&]() {
+      __threadfence_block();
       __syncwarp();
       if (lane == 0) {
-        sh.sdesc[s] = make_int4(total | (flags << 16), __float_as_int(mult), sl0, 0);
-        mbar_arrive(&sh.full_bar[s]);
+        Bm25Epoch& r = sh.epoch[epoch & (BM25_EPOCHS - 1)];
+        r.end_idx = widx;
+        __threadfence_block();
+        sts_volatile(&r.closed, epoch + 1);
       }
+      ++epoch;
       __syncwarp();
     };
     for (uint32_t gc = 0;; ++gc) {
       const uint32_t bb = gc & 1;
-      mbar_wait(&sh.bfull_bar[bb], (gc >> 1) & 1);
+      mbar_wait_lazy(&sh.bfull_bar[bb], (gc >> 1) & 1);
       const Bm25Group& G = sh.grp[bb];
-      if (G.kind != 0) { emit_ctrl(BM25_F_END, 0, 0, 0.f); break; }
+      if (G.kind != 0) { open_epoch(0, BM25_E_END, 0, 0, 0.f); close_epoch(); break; }
       const int nt = G.nt, ns = G.ns, chain = G.chain, step = G.step;
-      if (G.first) emit_ctrl(BM25_F_ITEM_BEGIN, step, chain, G.inv_scale);
+      if (G.first) { open_epoch(0, BM25_E_ITEM_BEGIN, chain, step, G.inv_scale); close_epoch(); }
       for (int j = 0; j < ns; ++j) {
-        const int sl0 = G.b0 + j * BM25_SLAB;
-        const int last_t = G.last_t[j];
-        if (last_t < 0) {
-          // no postings here; with negative impacts a slab of zero scores still has to be ranked
-          if (!p.nonneg) emit_ctrl(BM25_F_SLAB_END, 0, sl0, 0.f);
-          continue;
-        }
-        for (int t0 = 0; t0 <= last_t; t0 += 32) {
+        const int sl0 = G.b0 + j * SLAB;
+        // no postings here: nothing to do, unless impacts can be negative (a slab of zero scores is ranked then)
+        if (G.last_t[j] < 0 && p.nonneg) continue;
+        open_epoch(sl0, BM25_E_SLAB, chain, step, G.inv_scale);
+        for (int t0 = 0; t0 < nt; t0 += 32) {
           const int t = t0 + lane;
           int64_t first = 0; int cnt = 0; float mult = 0.f;
-          if (t <= last_t) {
+          if (t < nt) {
             const int lo = G.bound[t * (ns + 1) + j];
             cnt = G.bound[t * (ns + 1) + j + 1] - lo;
             first = G.t_start[t] + lo;
             mult = G.t_mult[t];
           }
-          uint32_t live = __ballot_sync(0xffffffffu, cnt > 0);
-          // short runs of a (single-batch) slab that share a multiplier travel together
-          uint32_t shorts = 0;
-          float short_mult = 0.f;
-          if (last_t < 32) {
-            const uint32_t cand_short = __ballot_sync(0xffffffffu, cnt > 0 && cnt <= BM25_GATHER_MAX);
-            if (__popc(cand_short) >= 2) {
-              short_mult = __shfl_sync(0xffffffffu, mult, __ffs(cand_short) - 1);
-              shorts = __ballot_sync(0xffffffffu, cnt > 0 && cnt <= BM25_GATHER_MAX && mult == short_mult);
-              if (__popc(shorts) < 2) shorts = 0;
+          // A run is cut at multiples of BM25_SEG postings counted from the 32-posting (128-byte) boundary at or below
+          // its first posting: every warp-wide load of a segment is one aligned 128-byte line.  Segments per term,
+          // exclusive prefix over the lanes:
+          const int head_skip = int(first & 31);
+          const int span = head_skip + cnt;
+          const int nseg = cnt > 0 ? (span + BM25_SEG - 1) / BM25_SEG : 0;
+          int incl = nseg;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+          const int pre = incl - nseg;
+          const int S = __shfl_sync(0xffffffffu, incl, 31);
+          for (int base = 0; base < S; base += 32) {
+            const int i = base + lane;
+            // owner term of segment i: the last lane whose prefix is <= i
+            int own = 0;
+#pragma unroll
+            for (int stp = 16; stp > 0; stp >>= 1) {
+              const int c = own + stp;
+              const int pv = __shfl_sync(0xffffffffu, pre, c & 31);
+              if (c < 32 && pv <= i) own = c;
+            }
+            const int64_t f = __shfl_sync(0xffffffffu, first, own);
+            const int sp = __shfl_sync(0xffffffffu, span, own);
+            const float m = __shfl_sync(0xffffffffu, mult, own);
+            const int pr = __shfl_sync(0xffffffffu, pre, own);
+            if (i < S) {
+              const int sj = i - pr;
+              const int64_t pos = (f & ~int64_t(31)) + int64_t(sj) * BM25_SEG;      // 32-aligned first slot
+              const int lo = sj == 0 ? int(f & 31) : 0;                             // slots [lo, hi) hold the run's postings
+              const int hi = min(BM25_SEG, sp - sj * BM25_SEG);
+              const int idx = widx + i;
+              const int slot = idx & (BM25_RING - 1), lap = idx / BM25_RING;
+              spin_shared(&sh.freelap[slot], lap, false);
+              int* r = reinterpret_cast<int*>(&sh.ring[slot]);
+              r[0] = int(uint32_t(pos)) | lo;
+              r[1] = int(uint32_t(pos >> 32) & 0xffffu) | ((hi - 1) << 16) | ((epoch & 255) << 24);
+              r[2] = __float_as_int(m);
+              __threadfence_block();
+              sts_volatile(r + 3, lap + 1);
             }
           }
-          live &= ~shorts;
-          const int last_run = shorts ? -1 : (last_t < 32 ? 31 - __clz(int(live)) : last_t);   // run that ends the slab
-          while (live) {
-            const int src = __ffs(live) - 1;
-            live &= live - 1;
-            int64_t pos = __shfl_sync(0xffffffffu, first, src);
-            int rem = __shfl_sync(0xffffffffu, cnt, src);
-            const float m = __shfl_sync(0xffffffffu, mult, src);
-            const int endflags = (t0 + src == last_run) ? BM25_F_SLAB_END : 0;
-            while (rem > 0) {
-              const int n = min(rem, BM25_CHUNK - int(pos & 3));
-              emit(pos, n, m, sl0, n == rem ? endflags : 0);
-              pos += n;
-              rem -= n;
-            }
-          }
-          if (shorts) emit_gather(shorts, first, cnt, short_mult, sl0, BM25_F_SLAB_END);
+          widx += S;
         }
+        close_epoch();
       }
-      if (G.last) emit_ctrl(BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), step, chain, 0.f);
+      if (G.last) { open_epoch(0, BM25_E_ITEM_END | (G.final_step ? BM25_E_FINAL : 0), chain, step, 0.f); close_epoch(); }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);
     }
   } else {
     // ===================== consumers =====================
     // Scores are accumulated in fixed point (int32, per-query power-of-two scale) with shared-memory
-    // integer atomics: adds commute exactly, so the terms of a slab need no ordering between them,
+    // integer atomics: adds commute exactly, so the segments of a slab need no ordering between them,
     // results do not depend on which warp ran first, and one ATOMS replaces a load / add / store.
-    int mx = INT_MIN;         // largest score this thread wrote into the current slab
-    float inv_scale = 1.f;    // fixed point -> fp32 score of the current item's query
-    int64_t range_end = 0;    // docs at or past the end of the chain's split are not ranked
-    int* acci = reinterpret_cast<int*>(acc);
-    const uint32_t acc_u32 = smem_u32(acc);
-    const uint32_t rid0 = smem_u32(ring_id) + tid * 4, rim0 = smem_u32(ring_imp) + tid * 4;
-    uint32_t s = 0, ph = 0;
+    // With non-negative impacts a doc's running score only grows, so the add that brings it to the query's
+    // running k-th best sees it happen in the atomic's return value and notes the doc in a short "hot" list: at
+    // the end of the slab only those docs are looked at (the slab is scanned in full only while there is no
+    // threshold yet, when the list overflows, or when impacts can be negative).
+    const uint32_t hot_u32 = smem_u32(sh.hot), hotc_u32 = smem_u32(&sh.hot_cnt);
+    Bm25Slab cur{smem_u32(acc), INT_MAX, 0};
+    int my_epoch = -1;        // epoch this warp is in
+
+    // one posting: add; returns the doc's running score
+    auto add_posting = [&](int doc, float imp, float ms) -> int {
+      const int vi = __float2int_rn(imp * ms);
+      return atoms_add_s32(cur.accb + 4u * uint32_t(doc), vi) + vi;
+    };
+    // note a doc whose running score reached the threshold (rare)
+    auto note_hot = [&](int doc) {
+      uint32_t at;
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(hotc_u32) : "memory");
+      if (at < uint32_t(BM25_HOT)) asm volatile("st.shared.s32 [%0], %1;" ::"r"(hot_u32 + 4u * at), "r"(doc) : "memory");
+      else cur.thr_i = INT_MAX;                                // overflow: the slab will be scanned in full
+    };
+
+    // the claim of the next descriptor is issued one segment ahead: its latency hides behind the adds
+    int next_idx = 0;
+    if (lane == 0) next_idx = atomicAdd(&sh.head, 1);
     for (;;) {
-      mbar_wait(&sh.full_bar[s], ph);
-      const int4 de = sh.sdesc[s];
-      const int n = de.x & 0xfff, flags = de.x >> 16, sl0 = de.z;
-      const float ms = __int_as_float(de.y);                      // term multiplicity x scale
-      const uint32_t accb = acc_u32 - 4u * uint32_t(sl0);        // accb + 4 * doc == &acc[doc - slab0]
-      const uint32_t rid = rid0 + s * (BM25_CHUNK * 4), rim = rim0 + s * (BM25_CHUNK * 4);
-      int d[BM25_PER_THREAD]; float v[BM25_PER_THREAD];
-      if (n == BM25_CHUNK) {
-        // whole stage: no predicates.  The stage is handed back as soon as it is in registers.
-#pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) { d[u] = lds_s32(rid + u * (BM25_CONSUMERS * 4)); v[u] = lds_f32(rim + u * (BM25_CONSUMERS * 4)); }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
-#pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) {
-          const int vi = __float2int_rn(v[u] * ms);
-          mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[u]), vi) + vi);
+      const int idx = __shfl_sync(0xffffffffu, next_idx, 0);
+      const int slot = idx & (BM25_RING - 1), lap = idx / BM25_RING;
+      const int* rw = reinterpret_cast<const int*>(&sh.ring[slot]);
+      // ---- until the descriptor is published, follow the epochs that close in front of it; then the epochs up to its own.
+      //      No posting is loaded before the warp is in the descriptor's epoch: the loop below keeps its sixteen loaded
+      //      values in registers only because no call lies between the loads and the adds. ----
+      int4 de = make_int4(0, 0, 0, 0);
+      bool got = false;
+      long long t0 = 0;
+      for (;;) {
+        if (!got && lds_volatile(rw + 3) == lap + 1) {
+          __threadfence_block();
+          asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(de.x), "=r"(de.y), "=r"(de.z), "=r"(de.w)
+                       : "r"(smem_u32(&sh.ring[slot])) : "memory");
+          __syncwarp();
+          if (lane == 0) {
+            sts_volatile(&sh.freelap[slot], lap + 1);
+            if (LRAG_BM25_CLAIM_AHEAD) next_idx = atomicAdd(&sh.head, 1);
+          }
+          got = true;
         }
-      } else if (n <= BM25_CONSUMERS) {
-        // short run (the usual partial stage): at most one posting per thread, and warps past the
-        // end of the run only hand the stage back
-        const int skip = (de.x >> 12) & 3;
-        const bool ok = tid < n;
-        if (ok) { d[0] = lds_s32(rid + skip * 4); v[0] = lds_f32(rim + skip * 4); }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
-        if (ok) {
-          const int vi = __float2int_rn(v[0] * ms);
-          mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[0]), vi) + vi);
+        bool walk;
+        if (got) {
+          walk = ((((de.y >> 24) & 0xff) - my_epoch) & 255) != 0;
+          if (!walk) break;
+        } else {
+          walk = my_epoch < 0;
+          if (!walk) {
+            const Bm25Epoch& r = sh.epoch[my_epoch & (BM25_EPOCHS - 1)];
+            if (lds_volatile(&r.closed) == my_epoch + 1) walk = idx >= lds_volatile(&r.end_idx);
+          }
+        }
+        if (walk) {
+          if (my_epoch >= 0) bm25_end_epoch(p, sh, my_epoch);
+          ++my_epoch;
+          cur = bm25_begin_epoch(p, sh, my_epoch);
+          if (cur.end) break;
+          t0 = 0;
+          continue;
+        }
+        __nanosleep(32);
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 20000000000LL) {
+          printf("lrag: bm25 descriptor wait timed out (block %d warp %d idx %d epoch %d)\n", blockIdx.x, warp, idx, my_epoch);
+          __trap();
+        }
+      }
+      if (cur.end) break;
+      // ---- the segment: 8 coalesced (doc, impact) loads per lane, then the adds ----
+      const int64_t base = int64_t(uint32_t(de.x) & ~31u) | (int64_t(de.y & 0xffff) << 32);
+      const int lo = de.x & 31, hi = ((de.y >> 16) & 0xff) + 1;
+      const float ms = __int_as_float(de.z);                       // term multiplicity x scale
+      const int32_t* pid = p.doc_id + base + lane;
+      const float* pim = p.impact + base + lane;
+      int d[BM25_SEG_PER_LANE]; float v[BM25_SEG_PER_LANE];
+      if (lo == 0 && hi == BM25_SEG) {
+#pragma unroll
+        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
+        int tot[BM25_SEG_PER_LANE];
+        int top = INT_MIN;
+#pragma unroll
+        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { tot[u] = add_posting(d[u], v[u], ms); top = max(top, tot[u]); }
+        if (top >= cur.thr_i) {                                  // one branch per eight postings; taken rarely
+#pragma unroll
+          for (int u = 0; u < BM25_SEG_PER_LANE; ++u)
+            if (tot[u] >= cur.thr_i) note_hot(d[u]);
         }
       } else {
-        const int skip = (de.x >> 12) & 3;
 #pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u) {
-          const bool ok = tid + u * BM25_CONSUMERS < n;
-          d[u] = ok ? lds_s32(rid + (skip + u * BM25_CONSUMERS) * 4) : -1;
-          v[u] = ok ? lds_f32(rim + (skip + u * BM25_CONSUMERS) * 4) : 0.f;
+        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) {
+          d[u] = -1; v[u] = 0.f;
+          const int sl = lane + 32 * u;
+          if (sl >= lo && sl < hi) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.empty_bar[s]);
 #pragma unroll
-        for (int u = 0; u < BM25_PER_THREAD; ++u)
-          if (d[u] >= 0) {
-            const int vi = __float2int_rn(v[u] * ms);
-            mx = max(mx, atoms_add_s32(accb + 4u * uint32_t(d[u]), vi) + vi);
-          }
+        for (int u = 0; u < BM25_SEG_PER_LANE; ++u)
+          if (d[u] >= 0 && add_posting(d[u], v[u], ms) >= cur.thr_i) note_hot(d[u]);
       }
-      if (++s == BM25_STAGES) { s = 0; ph ^= 1; }
-      if (flags == 0) continue;
-
-      if (flags & BM25_F_SLAB_END) {
-        const int64_t slab0 = sl0;
-        const int cnt_before = sh.cand_cnt;
-        const unsigned long long thr_key = sh.thr_key;
-        // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
-        const float thr_s = !thr_key ? -INFINITY
-                            : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
-        // every add of the slab is done behind this barrier; with negative impacts an untouched doc
-        // (score 0) can be a hit too
-        const bool hit = consumers_bar_or(!p.nonneg || float(mx) * inv_scale >= thr_s);
-        if (hit) {
-          // ---- scan the slab for candidates ----
-          // Coarse filter in the integer domain (no conversion for the ~all accumulators that cannot matter):
-          // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s.
-          int thr_i = INT_MIN;
-          if (thr_s > -INFINITY) {
-            const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
-            thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
-            if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
-          }
-          const int4* a4 = reinterpret_cast<const int4*>(acc);
-#pragma unroll 2
-          for (int i = 0; i < BM25_SLAB / 4 / BM25_CONSUMERS; ++i) {
-            const int idx = (tid + i * BM25_CONSUMERS) * 4;
-            const int4 s4 = a4[tid + i * BM25_CONSUMERS];
-            const bool any4 = max(max(s4.x, s4.y), max(s4.z, s4.w)) >= thr_i;
-            if (!__any_sync(0xffffffffu, any4)) continue;
-            const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int64_t doc = slab0 + idx + e;
-              bool want = (sv[e] >= thr_s) && (doc < range_end);
-              uint64_t key = 0;
-              if (want) { key = make_key(sv[e], uint32_t(doc)); want = key > thr_key; }
-              cand_append(want, key, cand, cap, &sh.cand_cnt);
-            }
-          }
-          cbar();
-          if (sh.cand_cnt > cap) {
-            // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
-            Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key};
-            const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
-            uint64_t keep[BM25_KEEP];     // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
-#pragma unroll
-            for (int i = 0; i < BM25_KEEP; ++i) {
-              const int idx = tid + i * BM25_CONSUMERS;
-              keep[i] = idx < cnt_before ? cand[idx] : 0ull;
-            }
-            cbar();
-            if (tid == 0) sh.cand_cnt = 0;
-            cbar();
-#pragma unroll
-            for (int i = 0; i < BM25_KEEP; ++i) {
-              const bool want = keep[i] != 0ull && keep[i] >= pivot;
-              cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
-            }
-            for (int i = tid; i < BM25_SLAB; i += BM25_CONSUMERS) {
-              const int64_t doc = slab0 + i;
-              uint64_t key = 0;
-              bool want = doc < range_end;
-              if (want) { key = make_key(float(acci[i]) * inv_scale, uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
-              cand_append(want, key, cand, cap, &sh.cand_cnt);
-            }
-            cbar();
-            if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
-            cbar();
-          }
-        }
-        // ---- re-zero the slab for the next one ----
-        float4* z4 = reinterpret_cast<float4*>(acc);
-#pragma unroll
-        for (int i = 0; i < BM25_SLAB / 4 / BM25_CONSUMERS; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mx = INT_MIN;
-        cbar();
-      }
-
-      if (flags & BM25_F_ITEM_BEGIN) {
-        // the previous item ended behind a barrier: the candidate buffer is free
-        const int chain = de.z, step = de.y;
-        inv_scale = __int_as_float(de.w);
-        const int split = chain % p.S;
-        range_end = min(p.N, int64_t(split + 1) * p.dps);
-        if (step == 0) {
-          if (tid == 0) { sh.cand_cnt = 0; sh.thr_key = thr_init; }
-        } else {
-          spin_until_ge(p.ws.cand_flag + chain, step);
-          const int cnt = __ldcg(p.ws.ch_cnt + chain);
-          const uint64_t* src = p.ws.ch_cand + size_t(chain) * cap;
-          for (int i = tid; i < cnt; i += BM25_CONSUMERS) cand[i] = __ldcg(src + i);
-          if (tid == 0) { sh.cand_cnt = cnt; sh.thr_key = __ldcg(p.ws.ch_thr + chain); }
-        }
-        cbar();
-      }
-      if (flags & BM25_F_ITEM_END) {
-        const int chain = de.z, step = de.y;
-        if (flags & BM25_F_FINAL) {
-          // ---- sorted top-k of the surviving candidates -> this chain's key list ----
-          const int ncand = min(sh.cand_cnt, cap);
-          Bm25Cands cands{cand, ncand};
-          const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
-          uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acc);      // the (zeroed) slab doubles as the sort buffer
-          const int P = p.P;
-          if (tid == 0) sh.sel.nsel = 0;
-          cbar();
-          for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
-            const uint64_t key = cand[i];
-            if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
-          }
-          cbar();
-          block_sort_desc(sortbuf, P, cbar);
-          uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
-          for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
-          cbar();
-          for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
-          cbar();
-        } else {
-          const int cnt = min(sh.cand_cnt, cap);
-          uint64_t* dst = p.ws.ch_cand + size_t(chain) * cap;
-          for (int i = tid; i < cnt; i += BM25_CONSUMERS) dst[i] = cand[i];
-          if (tid == 0) { p.ws.ch_cnt[chain] = cnt; p.ws.ch_thr[chain] = sh.thr_key; }
-          __threadfence();
-          cbar();
-          if (tid == 0) st_release(p.ws.cand_flag + chain, step + 1);
-        }
-      }
-      if (flags & BM25_F_END) break;
+      if (!LRAG_BM25_CLAIM_AHEAD && lane == 0) next_idx = atomicAdd(&sh.head, 1);
     }
   }
 }
@@ -750,39 +888,53 @@ bm25_merge_kernel(const uint64_t* keys, int nsplit, int k, int P, int64_t N, int
 }
 
 struct Bm25Plan {
-  int S, cap, P, TS, item_slabs, steps, nc;
+  int S, cap, P, TS, slab, item_slabs, steps, nc;
   int64_t dps;
   unsigned long long total_items;
   size_t smem, ws;
   size_t off[13];
 };
 
-static int g_item_slabs = 0;     // 0 = not yet initialised
-static int bm25_item_slabs() {
-  if (!g_item_slabs) {
-    const char* e = getenv("LRAG_BM25_ITEM_SLABS");   // tuning knob: docs per work item = value * 16384
-    const int v = e ? atoi(e) : BM25_DEFAULT_ITEM_SLABS;
-    g_item_slabs = (v < 1 || v > 4096) ? BM25_DEFAULT_ITEM_SLABS : v;
+// Tuning knob (process-wide, like the launch profiler: set it before serving, not concurrently with launches):
+// slabs per work item; 0 = derive from BM25_DEFAULT_ITEM_DOCS.
+static int g_item_slabs = -1;    // -1 = environment not read yet
+static int bm25_item_slabs(int slab) {
+  if (g_item_slabs < 0) {
+    const char* e = getenv("LRAG_BM25_ITEM_SLABS");
+    const int v = e ? atoi(e) : 0;
+    g_item_slabs = (v < 0 || v > 4096) ? 0 : v;
   }
-  return g_item_slabs;
+  if (g_item_slabs > 0) return g_item_slabs;
+  const int d = BM25_DEFAULT_ITEM_DOCS / slab;
+  return d < 1 ? 1 : d;
 }
+
+// Shared memory one of two resident CTAs of an SM can have: 228 KB per SM, 1 KB reserved per CTA.
+constexpr size_t BM25_SMEM_PER_CTA = (228 * 1024 - 2 * 1024) / 2;
 
 static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int sms) {
   Bm25Plan pl;
   pl.P = next_pow2(k);
   pl.cap = 2 * pl.P < 512 ? 512 : 2 * pl.P;         // <= 2048 = 4 * BM25_CONSUMERS
   pl.TS = int(max_query_terms < 1 ? 1 : (max_query_terms > BM25_MAXT ? BM25_MAXT : max_query_terms));
-  pl.item_slabs = bm25_item_slabs();
+  // the slab: as many docs as leave room for a second CTA on the SM, and no more than the shard has
+  const size_t fixed = size_t(pl.cap) * 8 + BM25_SH_BYTES;
+  int64_t slab = int64_t((BM25_SMEM_PER_CTA - fixed) / 4 / BM25_SLAB_STEP) * BM25_SLAB_STEP;
+  slab = std::min<int64_t>(slab, BM25_SLAB_MAX);
+  slab = std::min<int64_t>(slab, (std::max<int64_t>(N, 1) + BM25_SLAB_STEP - 1) / BM25_SLAB_STEP * BM25_SLAB_STEP);
+  slab = std::max<int64_t>(slab, BM25_SLAB_STEP);
+  pl.slab = int(slab);
+  pl.item_slabs = bm25_item_slabs(pl.slab);
   // few queries: split every query's doc range into independent chains so that the machine is full, with items
   // small enough that there is about one chain per resident CTA (equal doc ranges of one query are equal work)
   const int64_t resident = 2 * int64_t(sms);
   if (nq < 2 * resident) {
-    const int64_t nslab = (N + BM25_SLAB - 1) / BM25_SLAB;
+    const int64_t nslab = (N + slab - 1) / slab;
     int64_t want = (nslab * nq + resident - 1) / resident;
     if (want < 1) want = 1;
     if (want < pl.item_slabs) pl.item_slabs = int(want);
   }
-  const int64_t item_docs = int64_t(pl.item_slabs) * BM25_SLAB;
+  const int64_t item_docs = int64_t(pl.item_slabs) * slab;
   int64_t n_items = (N + item_docs - 1) / item_docs;
   if (n_items < 1) n_items = 1;
   int64_t S = 1;
@@ -795,7 +947,7 @@ static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int
   pl.steps = int(items_per_split);
   pl.nc = int(int64_t(nq) * S);
   pl.total_items = (unsigned long long)pl.steps * (unsigned long long)pl.nc;
-  pl.smem = size_t(BM25_SLAB) * 4 + BM25_RING_BYTES + size_t(pl.cap) * 8 + sizeof(Bm25Shared);
+  pl.smem = size_t(pl.slab) * 4 + fixed;
   size_t o = 0;
   auto take = [&](int i, size_t bytes) { pl.off[i] = o; o += align_up(bytes, 256); };
   take(0, 8);                                         // counter
@@ -821,7 +973,7 @@ using namespace lrag;
 
 extern "C" int lrag_bm25_set_item_slabs(int slabs) {
   LRAG_REQUIRE(slabs >= 0 && slabs <= 4096, "bm25_set_item_slabs: %d out of range (0 = default, max 4096)", slabs);
-  g_item_slabs = slabs ? slabs : BM25_DEFAULT_ITEM_SLABS;
+  g_item_slabs = slabs;
   return LRAG_OK;
 }
 
@@ -837,15 +989,15 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && k > 0 && k <= LRAG_MAX_K, "bm25_topk: need nq > 0 and 1 <= k <= %d (nq=%d k=%d)", LRAG_MAX_K, nq, k);
-  LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31) - BM25_SLAB, "bm25_topk: N=%lld out of range for one shard", (long long)N);
+  LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31) - BM25_SLAB_MAX, "bm25_topk: N=%lld out of range for one shard", (long long)N);
   LRAG_REQUIRE(V >= 0 && V < (int64_t(1) << 31) && nnz >= 0, "bm25_topk: V=%lld nnz=%lld out of range", (long long)V, (long long)nnz);
   LRAG_REQUIRE(max_query_terms >= 0 && max_query_terms <= LRAG_BM25_MAX_QUERY_TERMS,
                "bm25_topk: a query has %lld terms; at most %d are supported", (long long)max_query_terms,
                LRAG_BM25_MAX_QUERY_TERMS);
   LRAG_REQUIRE(indptr && q_indptr && out_score && out_id, "bm25_topk: null pointer");
   LRAG_REQUIRE(impact_bound >= 0.f && impact_bound < 3.0e38f, "bm25_topk: impact_bound must be a finite value >= max |impact|");
-  LRAG_REQUIRE((reinterpret_cast<uintptr_t>(doc_id) & 15) == 0 && (reinterpret_cast<uintptr_t>(impact) & 15) == 0,
-               "bm25_topk: doc_id and impact must be 16-byte aligned (bulk async copies)");
+  LRAG_REQUIRE((reinterpret_cast<uintptr_t>(doc_id) & 3) == 0 && (reinterpret_cast<uintptr_t>(impact) & 3) == 0,
+               "bm25_topk: doc_id and impact must be 4-byte aligned");
   const int sms = sm_count();
   const Bm25Plan pl = bm25_plan(N, nq, k, max_query_terms, sms);
   if (ws_bytes < pl.ws || !ws) { set_error("bm25_topk: workspace %zu < required %zu", ws_bytes, pl.ws); return LRAG_ENOSPC; }
@@ -854,7 +1006,7 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   Bm25Params p;
   p.indptr = indptr; p.doc_id = doc_id; p.impact = impact; p.V = V; p.nnz = nnz; p.q_indptr = q_indptr; p.q_term = q_term;
   p.N = N; p.dps = pl.dps; p.total_items = pl.total_items; p.nq = nq; p.k = k; p.nonneg = nonneg ? 1 : 0;
-  p.S = pl.S; p.cap = pl.cap; p.P = pl.P; p.TS = pl.TS; p.item_slabs = pl.item_slabs; p.steps = pl.steps; p.nc = pl.nc;
+  p.S = pl.S; p.cap = pl.cap; p.P = pl.P; p.TS = pl.TS; p.item_slabs = pl.item_slabs; p.steps = pl.steps; p.nc = pl.nc; p.slab = pl.slab;
   p.ws.counter = reinterpret_cast<unsigned long long*>(w + pl.off[0]);
   p.ws.cur_flag = reinterpret_cast<int*>(w + pl.off[1]);
   p.ws.cand_flag = reinterpret_cast<int*>(w + pl.off[2]);
@@ -870,10 +1022,11 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   p.ws.q_inv_scale = reinterpret_cast<float*>(w + pl.off[12]);
   p.impact_bound = impact_bound;
 
-  static size_t smem_set = 0;
-  if (pl.smem > smem_set) {
+  static size_t smem_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+  const int dev = device_slot();
+  if (pl.smem > smem_set[dev]) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(bm25_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem)));
-    smem_set = pl.smem;
+    smem_set[dev] = pl.smem;
   }
   int occ = 0;
   LRAG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem));

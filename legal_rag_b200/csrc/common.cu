@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
 }
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 bool initialised() { return g_device >= 0; }
+int device_slot() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+  return d % LRAG_MAX_DEVICES;
+}
 encode_tiled_fn tensor_map_encoder() { return g_encode; }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,

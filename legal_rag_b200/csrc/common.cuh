@@ -17,6 +17,10 @@ namespace lrag {
 void set_error(const char* fmt, ...);
 int sm_count();                 // cached by lrag_init (148 on B200)
 bool initialised();
+// Index of the calling thread's current device into per-device tables (cudaFuncSetAttribute is per device, so
+// "already set" flags must be too).
+constexpr int LRAG_MAX_DEVICES = 64;
+int device_slot();
 // driver entry point for cuTensorMapEncodeTiled, fetched through the runtime
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

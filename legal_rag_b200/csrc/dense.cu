@@ -372,10 +372,11 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tx, X, uint64_t(N), uint64_t(d), uint64_t(d), DENSE_BN, DENSE_BK);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+    const int dev = device_slot();
+    if (!attr_set[dev]) {
       LRAG_CHECK_CUDA(cudaFuncSetAttribute(dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM));
-      attr_set = true;
+      attr_set[dev] = true;
     }
     // Epochs: [0, e0), [e0, 4 e0), [4 e0, 16 e0), ... ; between two epochs every query's threshold is
     // tightened to its exact k-th best so far.  An epoch boundary is a multiple of lcm(grid, QB) tiles,

@@ -238,15 +238,19 @@ extern "C" int lrag_fuse_topk(const float* s_dense, const int64_t* i_dense, cons
   p.nch = i_colb ? 3 : (i_bm25 ? 2 : 1);
   int P = 32; while (P < p.nch * kc) P <<= 1;
   p.P = P;
-  p.H = P <= 1024 ? 2 * P : P;      // load factor <= 0.5 for the usual list lengths, <= 0.75 at kc = 1024 (shared memory)
+  // open-addressing table: load factor <= 0.5; only three channels of kc > 682 (P = 4096) take H = P, load <= 0.75,
+  // because 2 P slots would not fit in shared memory
+  auto smem_for = [&](int H) { return size_t(p.nch * kc) * (8 + 8 + 8 + 4) + size_t(P) * 8 + size_t(H) * (8 + 12) + 16; };
+  p.H = smem_for(2 * P) <= 227 * 1024 ? 2 * P : P;
   p.w[0] = w_dense; p.w[1] = w_bm25; p.w[2] = w_colb;
   p.alpha = alpha; p.min_final = min_final;
   p.out_score = out_score; p.out_id = out_id; p.out_breakdown = out_breakdown;
-  const size_t smem = size_t(p.nch * kc) * (8 + 8 + 8 + 4) + size_t(P) * 8 + size_t(p.H) * (8 + 12) + 16;
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
+  const size_t smem = smem_for(p.H);
+  static size_t smem_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+  const int dev = device_slot();
+  if (smem > 48 * 1024 && smem > smem_set[dev]) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    smem_set = smem;
+    smem_set[dev] = smem;
   }
   prof_begin(static_cast<cudaStream_t>(stream), PROF_FUSE);
   fuse_kernel<<<nq, FUSE_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(p);

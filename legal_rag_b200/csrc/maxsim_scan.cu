@@ -277,10 +277,11 @@ static int scan_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld,
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&td, D, uint64_t(Nd) * Ld, SC_DIM, SC_DIM, SC_BN, SC_BK);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+  const int dev = device_slot();
+  if (!attr_set[dev]) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(maxsim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SC_SMEM));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int sms = sm_count();
   int64_t nchunks = (int64_t(sms) * 64 + p.QB - 1) / p.QB;             // about 64 units per CTA

@@ -6,20 +6,17 @@
 //   lrag_topk_merge       <- no reference counterpart (the reference is single-process)
 #include "select.cuh"
 #include <algorithm>
+#include <climits>
 
 namespace lrag {
 
 struct RowScores {
   const float* s; const int64_t* col_id; int64_t n;
   template <class F> __device__ void operator()(F&& f) const {
+    // the tie field is the column: with column ids the id (any width) is looked up when the hit is written
     for (int64_t c = threadIdx.x; c < n; c += SELECT_THREADS) {
-      uint32_t tie = uint32_t(c);
-      if (col_id) {
-        const int64_t id = col_id[c];
-        if (id < 0) continue;
-        tie = uint32_t(id);
-      }
-      f(make_key(s[c], tie));
+      if (col_id && col_id[c] < 0) continue;
+      f(make_key(s[c], uint32_t(c)));
     }
   }
 };
@@ -32,15 +29,18 @@ topk_select_kernel(const float* S, int64_t ld, int64_t N, int k, int64_t id_base
   const int q = blockIdx.x;
   RowScores rows{S + size_t(q) * ld, col_id ? col_id + size_t(q) * N : nullptr, N};
   block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), id_base,
-                    out_score + size_t(q) * k, out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr));
+                    out_score + size_t(q) * k, out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), rows.col_id);
 }
 
+// (score, id) pairs of one row.  Narrow rows (max id - min id < 2^32 - 1: every sharded corpus below 4 G docs) keep the
+// exact (score desc, id asc) order through the key's tie field = id - min id; wider rows key on the entry index and
+// look the 64-bit id up when the hit is written.
 struct RowPairs {
-  const float* s; const int64_t* id; int n;
+  const float* s; const int64_t* id; int n; int64_t base; bool wide;
   template <class F> __device__ void operator()(F&& f) const {
     for (int c = threadIdx.x; c < n; c += SELECT_THREADS) {
       const int64_t i = id[c];
-      if (i >= 0) f(make_key(s[c], uint32_t(i)));
+      if (i >= 0) f(make_key(s[c], wide ? uint32_t(c) : uint32_t(i - base)));
     }
   }
 };
@@ -49,10 +49,27 @@ __global__ void __launch_bounds__(SELECT_THREADS)
 topk_merge_kernel(const float* score, const int64_t* id, int L, int k, int P, float* out_score, int64_t* out_id) {
   extern __shared__ uint8_t sm_raw[];
   __shared__ SelectShared ss;
+  __shared__ long long id_min, id_max;
   const int q = blockIdx.x;
-  RowPairs rows{score + size_t(q) * L, id + size_t(q) * L, L};
-  block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), 0, out_score + size_t(q) * k,
-                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr));
+  const int64_t* ids = id + size_t(q) * L;
+  if (threadIdx.x == 0) { id_min = LLONG_MAX; id_max = -1; }
+  __syncthreads();
+  long long lo = LLONG_MAX, hi = -1;
+  for (int c = threadIdx.x; c < L; c += SELECT_THREADS) {
+    const long long i = ids[c];
+    if (i >= 0) { lo = i < lo ? i : lo; hi = i > hi ? i : hi; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(&id_min, lo); atomicMax(&id_max, hi); }
+  __syncthreads();
+  const bool wide = id_max >= 0 && (unsigned long long)(id_max - id_min) >= 0xffffffffull;
+  RowPairs rows{score + size_t(q) * L, ids, L, id_max >= 0 ? id_min : 0, wide};
+  block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), rows.base, out_score + size_t(q) * k,
+                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), wide ? ids : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -100,10 +117,8 @@ struct SliceFilter {
   // one score that reached the threshold: make its key, append it.  `col` = its column in the row, `cid` = the row's
   // column ids (or null; a negative id marks a column that does not take part)
   __device__ __forceinline__ void offer(float s, uint32_t col, const int64_t* cid) {
-    uint32_t tie = col;
-    bool ok = true;
-    if (cid) { const int64_t id = cid[col]; ok = id >= 0; tie = uint32_t(id); }
-    const uint64_t key = make_key(s, tie);
+    const bool ok = !cid || cid[col] >= 0;
+    const uint64_t key = make_key(s, col);                   // the tie field is the column; ids are looked up at the end
     if (ok && key > thr_key) {
       // one plain shared-memory atomic per hit: hits are rare and scattered over the warp, so the vote / popc / shuffle
       // sequence of a warp-aggregated increment (what atomicAdd compiles to) costs more than it saves
@@ -364,7 +379,8 @@ struct KeyList {
 };
 
 __global__ void __launch_bounds__(SELECT_THREADS)
-topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id_base, float* out_score, int64_t* out_id, StreamPlan plan) {
+topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id_base, float* out_score, int64_t* out_id, StreamPlan plan,
+                       const int64_t* col_id, int64_t N) {
   extern __shared__ uint8_t sm_raw[];
   __shared__ SelectShared ss;
   const int q = blockIdx.x;
@@ -373,7 +389,7 @@ topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id
     lists = ((q + 1) * plan.tpr - 1) / plan.seg_trips - (q * plan.tpr) / plan.seg_trips + 1;
   KeyList rows{keys + size_t(q) * slots * k, lists * k};
   block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), id_base, out_score + size_t(q) * k,
-                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr));
+                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), col_id ? col_id + size_t(q) * N : nullptr);
 }
 
 // Slice length of the fixed-slice path: 2^18 scores when that already gives every SM several CTAs, shorter (down to 2^15, a
@@ -423,12 +439,13 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
                        float* out_score, int64_t* out_id, cudaStream_t stream, void* ws, size_t ws_bytes) {
   const int P = next_pow2(k);
   const size_t smem_slice = size_t(SELECT_CAP + P) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+  const int dev = device_slot();
+  if (!attr_set[dev]) {
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(stream_smem_bytes(LRAG_MAX_K, 4096))));
     LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (SELECT_CAP + LRAG_MAX_K) * 8));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   uint64_t* keys = static_cast<uint64_t*>(ws);
   StreamPlan plan{};
@@ -438,7 +455,7 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
     topk_stream_kernel<<<plan.grid, STREAM_THREADS, stream_smem_bytes(k, plan.trig), stream>>>(S, ld, N, k, col_id, plan, keys);
     prof_end(stream);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
-    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, plan.spr, k, P, id_base, out_score, out_id, plan);
+    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, plan.spr, k, P, id_base, out_score, out_id, plan, col_id, N);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
     return LRAG_OK;
   }
@@ -450,7 +467,7 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
     topk_slice_kernel<<<dim3(nslices, nq), SELECT_THREADS, smem_slice, stream>>>(S, ld, N, k, P, col_id, slice_len, nslices, keys);
     prof_end(stream);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
-    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, nslices, k, P, id_base, out_score, out_id, StreamPlan{});
+    topk_merge_keys_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), stream>>>(keys, nslices, k, P, id_base, out_score, out_id, StreamPlan{}, col_id, N);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
     return LRAG_OK;
   }

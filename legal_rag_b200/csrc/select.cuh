@@ -107,9 +107,14 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* key, int P, Bar bar = 
 // Exact sorted top-k of the candidates `for_each` enumerates.  sel_key: shared, P = pow2 >= k.
 // Returns (in every thread) the number of real hits written; rows are padded with
 // (LRAG_PAD_SCORE, -1).  out_key, if non-null, receives the k winning keys (0 = empty).
+// `lookup` == null: a key's tie field is a local id and the hit's id is id_base + that.
+// `lookup` != null: the tie field is an index into `lookup` (ids of any width; 64-bit ids never pass through
+// the 32-bit field): the hit's id is lookup[index], and hits of equal score are put in ascending id order
+// afterwards (which of several equal scores make the cut at rank k is then decided by index, not by id).
 template <class ForEach>
 __device__ int block_topk_sorted(const ForEach& for_each, int k, int P, SelectShared& sm, uint64_t* sel_key,
-                                 int64_t id_base, float* out_score, int64_t* out_id, uint64_t* out_key) {
+                                 int64_t id_base, float* out_score, int64_t* out_id, uint64_t* out_key,
+                                 const int64_t* lookup = nullptr) {
   const int tid = threadIdx.x;
   const unsigned long long pivot = block_select_pivot(for_each, k, sm);
   for (int i = tid; i < P; i += SELECT_THREADS) sel_key[i] = 0;
@@ -126,10 +131,23 @@ __device__ int block_topk_sorted(const ForEach& for_each, int k, int P, SelectSh
   for (int r = tid; r < k; r += SELECT_THREADS) {
     const uint64_t key = (r < n) ? sel_key[r] : 0;
     if (out_key) out_key[r] = key;
-    if (out_score) {
-      out_score[r] = key ? key_score(key) : LRAG_PAD_SCORE;
-      out_id[r] = key ? id_base + int64_t(key_id(key)) : -1;
+    if (!out_score) continue;
+    if (!key) { out_score[r] = LRAG_PAD_SCORE; out_id[r] = -1; continue; }
+    if (!lookup) { out_score[r] = key_score(key); out_id[r] = id_base + int64_t(key_id(key)); continue; }
+    // rank inside the run of equal scores by (id, index): runs are one hit long unless scores tie exactly
+    const uint32_t so = uint32_t(key >> 32);
+    const int64_t id = lookup[key_id(key)];
+    int lo = r, hi = r;
+    while (lo > 0 && uint32_t(sel_key[lo - 1] >> 32) == so) --lo;
+    while (hi + 1 < n && uint32_t(sel_key[hi + 1] >> 32) == so) ++hi;
+    int pos = lo;
+    for (int j = lo; j <= hi; ++j) {
+      if (j == r) continue;
+      const int64_t idj = lookup[key_id(sel_key[j])];
+      pos += (idj < id || (idj == id && j < r)) ? 1 : 0;
     }
+    out_score[pos] = key_score(key);
+    out_id[pos] = id;
   }
   __syncthreads();
   return n;
