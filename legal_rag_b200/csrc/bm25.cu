@@ -21,26 +21,25 @@
 //                      boundaries of every query term at every slab edge with one parallel round of
 //                      windowed binary searches (postings are doc-id sorted); double-buffered, one
 //                      group of slabs ahead of the emit warp;
-//   * emit warp     -- turns the (slab, term) runs into *segment descriptors* {first posting, count <=
-//                      BM25_SEG, term multiplicity x scale} in a shared-memory descriptor ring (the lanes
-//                      write the segments of a slab in parallel), and keeps a small ring of *epoch
-//                      records*: an epoch is one slab visit (or an item's begin / end control point);
-//                      a record says where the epoch's descriptors end;
-//   * 16 consumer warps -- each claims the next descriptor (one shared-memory atomic per warp), loads the
-//                      segment's (doc, impact) pairs straight from global memory / L2 into registers
-//                      (coalesced 4-byte loads, L1 no-allocate: no shared-memory staging, no per-stage
-//                      hand-shake between warps) and adds `mult * impact` into acc[doc - slab0] with one
+//   * emit warp     -- publishes one small *slab table* per slab in a shared-memory ring: per query term the run of
+//                      postings that falls into the slab {first posting, count, multiplicity x scale} and the
+//                      prefix of the runs' chunk counts (a chunk = 256 postings starting at a 128-byte boundary of
+//                      the posting arrays), plus flags {end of slab | item begin | item end};
+//   * 16 consumer warps -- each reads the table and takes the chunks c = warp, warp + 16, ... of the slab: every warp
+//                      makes the same number of trips to memory (+-1) and nobody claims anything.  A chunk's
+//                      (doc, impact) pairs are loaded straight from global memory / L2 into registers
+//                      (coalesced 4-byte loads: no shared-memory staging, no per-stage
+//                      hand-shake between warps) and added into acc[doc - slab0] with one
 //                      shared-memory integer atomic per posting: scores are kept in fixed point (int32, a
 //                      per-query power-of-two scale sized from `impact_bound`), so adds commute exactly, the
-//                      segments of a slab need no ordering between them and the result is independent
-//                      of scheduling.  Each thread keeps a running max of what it wrote.  A warp whose
-//                      claimed descriptor lies past the end of the current epoch goes to the epoch's end:
-//                      one `bar.red.or` tells whether any thread wrote a score that reaches
-//                      the query's running k-th best; only then is the slab scanned for candidates
-//                      (appended to a shared buffer; an overflow triggers an exact radix select that
-//                      raises the threshold).  The slab is re-zeroed.  The loads of the next epoch's first
-//                      segment are already in flight while the warp sits in those barriers.
-//                      Item-begin / item-end epochs load / store the chain's candidate state; the
+//                      chunks of a slab need no ordering between them and the result is independent
+//                      of scheduling.  With non-negative impacts a doc's running score only grows: the add that
+//                      brings it to the query's running k-th best sees that in the atomic's return value and
+//                      notes the doc in a short "hot" list.  At the end of the slab the warps meet at a barrier and
+//                      only the hot docs are looked at (the slab is scanned in full only while there is no
+//                      threshold yet, when the list overflows, or when impacts can be negative; an overflow of the
+//                      candidate buffer triggers an exact radix select that raises the threshold).  The slab is
+//                      re-zeroed.  Item-begin / item-end tables load / store the chain's candidate state; the
 //                      chain's last item sorts its top-k into the per-chain key list.
 // Round 1 staged postings through a bulk-copy ring that all 16 warps consumed stage by stage: 44 warp
 // instructions and 10 shared-memory wavefronts per 32 postings (ring write + ring read + atomic + the
@@ -58,7 +57,10 @@
 
 namespace lrag {
 
-constexpr int BM25_CONSUMERS = 512;                  // 16 warps
+#ifndef LRAG_BM25_CONSUMERS
+#define LRAG_BM25_CONSUMERS 512
+#endif
+constexpr int BM25_CONSUMERS = LRAG_BM25_CONSUMERS;  // consumer threads
 constexpr int BM25_THREADS = BM25_CONSUMERS + 64;    // consumers, emit warp, bounds warp
 constexpr int BM25_SLAB_STEP = 4 * BM25_CONSUMERS;   // slab sizes are multiples of one int4 per consumer thread
 constexpr int BM25_SLAB_MAX = 12 * BM25_SLAB_STEP;   // 24 576 docs = 96 KB
@@ -68,21 +70,15 @@ constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
 #ifndef LRAG_BM25_SEG
 #define LRAG_BM25_SEG 256
 #endif
-#ifndef LRAG_BM25_CLAIM_AHEAD
-#define LRAG_BM25_CLAIM_AHEAD 1
-#endif
-#ifndef LRAG_BM25_HOTLIST
-#define LRAG_BM25_HOTLIST 1
-#endif
 constexpr int BM25_SEG = LRAG_BM25_SEG;              // postings per segment descriptor (8 per lane)
 constexpr int BM25_SEG_PER_LANE = BM25_SEG / 32;
-constexpr int BM25_RING = 128;                       // segment descriptors in flight
-constexpr int BM25_EPOCHS = 16;                      // epoch records in flight
+constexpr int BM25_TABS = 4;                         // slab tables in flight
+constexpr int BM25_WARPS = BM25_CONSUMERS / 32;
 constexpr int BM25_HOT = 512;                        // docs per slab whose running score reached the threshold (more: full scan)
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 constexpr int BM25_DEFAULT_ITEM_DOCS = 32 * 12288;   // docs per work item (the item is a whole number of slabs)
-enum : int { BM25_E_SLAB = 1, BM25_E_ITEM_BEGIN = 2, BM25_E_ITEM_END = 4, BM25_E_FINAL = 8, BM25_E_END = 16 };
+enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
 
 struct Bm25Ws {
   unsigned long long* counter;     // next item
@@ -122,26 +118,22 @@ struct Bm25Group {                 // bounds warp -> emit warp
   int32_t last_t[BM25_MAX_GROUP];  // last term with postings in the slab, -1 = none
 };
 
-// One epoch = one slab visit or one control point of an item.  Written by the emit warp: the fields, then
-// `pub` = epoch + 1; after the epoch's last descriptor `end_idx` (index of the first descriptor of any later
-// epoch), then `closed` = epoch + 1.  The slot of epoch e is reused for e + BM25_EPOCHS once the consumers
-// have set `epochs_done` past e.
-struct Bm25Epoch {
-  int slab0, flags, chain, step;
-  float inv_scale;
-  int end_idx;
-  int pub, closed;
+// One slab's work (<= 32 runs; a query with more terms takes several tables per slab) or a bare marker, written by
+// the emit warp.  `tag` (lap + 1) is written last and publishes the table; every consumer warp adds one to `arrived`
+// once it holds the table in registers, and the slot is rewritten when all have.
+struct alignas(16) Bm25Tab {
+  int flags, slab0, nruns, nchunks;
+  int chain, step; float inv_scale; int tag;
+  int arrived, pad[3];
+  int first_lo[32], first_hi[32], cnt[32], cpre[32];     // per run: first posting, count, chunks of the runs before it
+  float mult[32];                                         // occurrences in the query x the query's fixed-point scale
 };
 
 struct Bm25Shared {
   SelectShared sel;
-  int4 ring[BM25_RING];            // {base lo | lo slot, base hi(16) | (hi slot - 1) << 16 | (epoch & 255) << 24, mult x scale bits, lap + 1}
+  Bm25Tab tab[BM25_TABS];
   int hot[BM25_HOT];               // docs of the current slab whose running score reached the threshold
   int hot_cnt;
-  int freelap[BM25_RING];          // lap for which the slot may be written next
-  Bm25Epoch epoch[BM25_EPOCHS];
-  int head;                        // next descriptor index to claim
-  int epochs_done;                 // epochs the consumers have left behind
   uint64_t bfull_bar[2], bempty_bar[2];                      // group buffers
   Bm25Group grp[2];
   int64_t t_start[BM25_MAXT];      // bounds warp's view of the current item's query
@@ -163,12 +155,14 @@ __device__ __forceinline__ int lower_bound_doc(const int32_t* __restrict__ ids, 
   return lo;
 }
 
-// streaming 4-byte loads of postings: read-only path, no L1 allocation (every posting is used once per CTA)
+// Streaming 4-byte loads of postings.  Every posting is used once per CTA but by many CTAs at about the same time, so it
+// must stay in L2 and has no business in L1: ld.global.cg.  (Measured at the hybrid shape: `.nc.L1::no_allocate` reads
+// every posting ~10 times from DRAM -- 27 GB against 2.2 GB, L2 hit rate 82 % against 97 % -- and is 9 % slower.)
 __device__ __forceinline__ int ldg_stream_s32(const int32_t* p) {
-  int v; asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
+  int v; asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v;
 }
 __device__ __forceinline__ float ldg_stream_f32(const float* p) {
-  float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+  float v; asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
 }
 // shared-memory words that another warp of the CTA publishes
 __device__ __forceinline__ int lds_volatile(const int* p) {
@@ -336,199 +330,191 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Epoch changes of the consumer warps.  Kept out of line: the segment loop holds sixteen loaded postings in
-// registers while a warp changes epochs, and this code (barriers, candidate selection, chain state) must not
-// take part in that loop's register allocation.
+// What the consumer warps do at a marker.  Kept out of line: the chunk loop holds sixteen loaded postings in
+// registers, and this code (barriers, candidate selection, chain state) must not take part in that loop's register
+// allocation.  Each returns the fixed-point threshold at or above which an add notes its doc (INT_MAX: never).
 // ------------------------------------------------------------------------------------------------
-struct Bm25Slab { uint32_t accb; int thr_i; int end; };      // what the segment loop needs from an epoch
+__device__ __forceinline__ int bm25_note_threshold(const Bm25Params& p, const Bm25Shared& sh) {
+  if (!p.nonneg) return INT_MAX;             // negative impacts: every slab is scanned in full anyway
+  const unsigned long long thr_key = sh.thr_key;
+  // "strictly positive" while fewer than k docs have been seen (zero scores are filled in by the merge)
+  const float thr_s = (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+  const float t = thr_s / sh.inv_scale;      // a lower bound of every fixed-point value whose fp32 score reaches thr_s
+  const int thr_i = t >= 2147483520.f ? INT_MAX : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1;
+  return thr_i < 1 ? 1 : thr_i;
+}
 
-// Leaves epoch `e`: ranks the slab's hot docs (or the whole slab), re-zeroes it, stores the chain state at an item's end.
-__device__ __noinline__ void bm25_end_epoch(const Bm25Params& p, Bm25Shared& sh, int e) {
+// End of a slab: ranks the slab's hot docs (or the whole slab) and re-zeroes it.
+__device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, int slab0_, int thr_note) {
   const int tid = threadIdx.x;
   const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
   const int SLAB = p.slab, cap = p.cap;
   int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
   uint64_t* cand = reinterpret_cast<uint64_t*>(acci + SLAB);
-  const Bm25Epoch& r = sh.epoch[e & (BM25_EPOCHS - 1)];
-  const int ep_flags = r.flags, ep_chain = r.chain, ep_step = r.step;
-  const int64_t slab0 = r.slab0;
+  const int64_t slab0 = slab0_;
   const float inv_scale = sh.inv_scale;
   const int64_t range_end = sh.range_end;
-  bool synced = false;
-  if (ep_flags & BM25_E_SLAB) {
-    cbar();                                                 // every add of the slab is done
-    const int cnt_before = sh.cand_cnt;
-    const unsigned long long thr_key = sh.thr_key;
-    const int nh = sh.hot_cnt;
-    // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
-    const float thr_s = !thr_key ? -INFINITY
-                        : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
-    // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s
-    int thr_i = INT_MIN;
-    if (thr_s > -INFINITY) {
-      const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
-      thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
-      if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
-    }
-    if (LRAG_BM25_HOTLIST && p.nonneg && nh <= BM25_HOT && cnt_before + nh <= cap) {
-      if (nh > 0) {
-        // ---- the hot docs: final score -> candidate (a doc noted twice is taken once: the read clears it) ----
-        for (int i0 = 0; i0 < nh; i0 += BM25_CONSUMERS) {
-          const int i = i0 + tid;
-          bool want = false;
-          uint64_t key = 0;
-          if (i < nh) {
-            const int doc = sh.hot[i];
-            const int val = atomicExch(acci + (doc - int(slab0)), 0);
-            const float sc = float(val) * inv_scale;
-            want = val >= thr_i && sc >= thr_s && int64_t(doc) < range_end;
-            if (want) { key = make_key(sc, uint32_t(doc)); want = key > thr_key; }
-          }
-          if (i0 + (tid & ~31) < nh) cand_append(want, key, cand, cap, &sh.cand_cnt);
-        }
-        cbar();                                             // hot docs are read before the slab is cleared
-      }
-    } else {
-      // ---- scan the slab for candidates ----
-      const int4* a4 = reinterpret_cast<const int4*>(acci);
-#pragma unroll 2
-      for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) {
-        const int idx = (tid + i * BM25_CONSUMERS) * 4;
-        const int4 s4 = a4[tid + i * BM25_CONSUMERS];
-        const bool any4 = max(max(s4.x, s4.y), max(s4.z, s4.w)) >= thr_i;
-        if (!__any_sync(0xffffffffu, any4)) continue;
-        const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
-#pragma unroll
-        for (int el = 0; el < 4; ++el) {
-          const int64_t doc = slab0 + idx + el;
-          bool want = (sv[el] >= thr_s) && (doc < range_end);
-          uint64_t key = 0;
-          if (want) { key = make_key(sv[el], uint32_t(doc)); want = key > thr_key; }
-          cand_append(want, key, cand, cap, &sh.cand_cnt);
-        }
-      }
-      cbar();
-      if (sh.cand_cnt > cap) {
-        // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
-        Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key, SLAB};
-        const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
-        uint64_t keep[BM25_KEEP];     // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
-#pragma unroll
-        for (int i = 0; i < BM25_KEEP; ++i) {
-          const int idx = tid + i * BM25_CONSUMERS;
-          keep[i] = idx < cnt_before ? cand[idx] : 0ull;
-        }
-        cbar();
-        if (tid == 0) sh.cand_cnt = 0;
-        cbar();
-#pragma unroll
-        for (int i = 0; i < BM25_KEEP; ++i) {
-          const bool want = keep[i] != 0ull && keep[i] >= pivot;
-          cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
-        }
-        for (int i = tid; i < SLAB; i += BM25_CONSUMERS) {
-          const int64_t doc = slab0 + i;
-          uint64_t key = 0;
-          bool want = doc < range_end;
-          if (want) { key = make_key(float(acci[i]) * inv_scale, uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
-          cand_append(want, key, cand, cap, &sh.cand_cnt);
-        }
-        cbar();
-        if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
-        cbar();
-      }
-    }
-    // ---- re-zero the slab for the next one ----
+  cbar();                                                 // every add of the slab is done
+  const int nh = sh.hot_cnt;
+  if (p.nonneg && nh == 0) {
+    // nothing reached the threshold (the usual case once a few slabs have been seen): clear the slab, keep the threshold
     float4* z4 = reinterpret_cast<float4*>(acci);
 #pragma unroll 4
     for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) sh.hot_cnt = 0;
     cbar();
-    synced = true;
+    return thr_note;
   }
-  if (ep_flags & BM25_E_ITEM_END) {
-    const int chain = ep_chain, step = ep_step;
-    if (ep_flags & BM25_E_FINAL) {
-      // ---- sorted top-k of the surviving candidates -> this chain's key list ----
-      const int ncand = min(sh.cand_cnt, cap);
-      Bm25Cands cands{cand, ncand};
-      const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
-      uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acci);     // the (zeroed) slab doubles as the sort buffer
-      const int P = p.P;
-      if (tid == 0) sh.sel.nsel = 0;
-      cbar();
-      for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
-        const uint64_t key = cand[i];
-        if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
+  const int cnt_before = sh.cand_cnt;
+  const unsigned long long thr_key = sh.thr_key;
+  // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
+  const float thr_s = !thr_key ? -INFINITY
+                      : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+  // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s
+  int thr_i = INT_MIN;
+  if (thr_s > -INFINITY) {
+    const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
+    thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
+    if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
+  }
+  if (p.nonneg && nh <= BM25_HOT && cnt_before + nh <= cap) {
+    if (nh > 0) {
+      // ---- the hot docs: final score -> candidate (a doc noted twice is taken once: the read clears it) ----
+      for (int i0 = 0; i0 < nh; i0 += BM25_CONSUMERS) {
+        const int i = i0 + tid;
+        bool want = false;
+        uint64_t key = 0;
+        if (i < nh) {
+          const int doc = sh.hot[i];
+          const int val = atomicExch(acci + (doc - int(slab0)), 0);
+          const float sc = float(val) * inv_scale;
+          want = val >= thr_i && sc >= thr_s && int64_t(doc) < range_end;
+          if (want) { key = make_key(sc, uint32_t(doc)); want = key > thr_key; }
+        }
+        if (i0 + (tid & ~31) < nh) cand_append(want, key, cand, cap, &sh.cand_cnt);
+      }
+      cbar();                                             // hot docs are read before the slab is cleared
+    }
+  } else {
+    // ---- scan the slab for candidates ----
+    const int4* a4 = reinterpret_cast<const int4*>(acci);
+#pragma unroll 2
+    for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) {
+      const int idx = (tid + i * BM25_CONSUMERS) * 4;
+      const int4 s4 = a4[tid + i * BM25_CONSUMERS];
+      const bool any4 = max(max(s4.x, s4.y), max(s4.z, s4.w)) >= thr_i;
+      if (!__any_sync(0xffffffffu, any4)) continue;
+      const float sv[4] = {float(s4.x) * inv_scale, float(s4.y) * inv_scale, float(s4.z) * inv_scale, float(s4.w) * inv_scale};
+#pragma unroll
+      for (int el = 0; el < 4; ++el) {
+        const int64_t doc = slab0 + idx + el;
+        bool want = (sv[el] >= thr_s) && (doc < range_end);
+        uint64_t key = 0;
+        if (want) { key = make_key(sv[el], uint32_t(doc)); want = key > thr_key; }
+        cand_append(want, key, cand, cap, &sh.cand_cnt);
+      }
+    }
+    cbar();
+    if (sh.cand_cnt > cap) {
+      // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
+      Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key, SLAB};
+      const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
+      uint64_t keep[BM25_KEEP];     // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
+#pragma unroll
+      for (int i = 0; i < BM25_KEEP; ++i) {
+        const int idx = tid + i * BM25_CONSUMERS;
+        keep[i] = idx < cnt_before ? cand[idx] : 0ull;
       }
       cbar();
-      block_sort_desc(sortbuf, P, cbar);
-      uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
-      for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
+      if (tid == 0) sh.cand_cnt = 0;
       cbar();
-      for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
+#pragma unroll
+      for (int i = 0; i < BM25_KEEP; ++i) {
+        const bool want = keep[i] != 0ull && keep[i] >= pivot;
+        cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
+      }
+      for (int i = tid; i < SLAB; i += BM25_CONSUMERS) {
+        const int64_t doc = slab0 + i;
+        uint64_t key = 0;
+        bool want = doc < range_end;
+        if (want) { key = make_key(float(acci[i]) * inv_scale, uint32_t(doc)); want = (key > thr_key) && (key >= pivot); }
+        cand_append(want, key, cand, cap, &sh.cand_cnt);
+      }
       cbar();
-    } else {
-      const int cnt = min(sh.cand_cnt, cap);
-      uint64_t* dst = p.ws.ch_cand + size_t(chain) * cap;
-      for (int i = tid; i < cnt; i += BM25_CONSUMERS) dst[i] = cand[i];
-      if (tid == 0) { p.ws.ch_cnt[chain] = cnt; p.ws.ch_thr[chain] = sh.thr_key; }
-      __threadfence();
+      if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
       cbar();
-      if (tid == 0) st_release(p.ws.cand_flag + chain, step + 1);
     }
-    synced = true;
   }
-  if (!synced) cbar();      // every thread has stopped reading this epoch's record
-  if (tid == 0) sts_volatile(&sh.epochs_done, e + 1);
+  // ---- re-zero the slab for the next one ----
+  float4* z4 = reinterpret_cast<float4*>(acci);
+#pragma unroll 4
+  for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) sh.hot_cnt = 0;
+  cbar();
+  return bm25_note_threshold(p, sh);
 }
 
-// Enters epoch `e`: loads the chain state at an item's begin; returns the slab's accumulator base and the fixed-point
-// threshold above which an add notes its doc (INT_MAX: never), and whether this is the END epoch.
-__device__ __noinline__ Bm25Slab bm25_begin_epoch(const Bm25Params& p, Bm25Shared& sh, int e) {
+// Begin of an item: the chain's candidate state (from the workspace after the first step).
+__device__ __noinline__ int bm25_item_begin(const Bm25Params& p, Bm25Shared& sh, int chain, int step, float inv_scale) {
   const int tid = threadIdx.x;
   const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
   const int cap = p.cap;
   int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
   uint64_t* cand = reinterpret_cast<uint64_t*>(acci + p.slab);
-  const Bm25Epoch& r = sh.epoch[e & (BM25_EPOCHS - 1)];
-  if ((tid & 31) == 0) spin_shared(&r.pub, e + 1, false);
-  __syncwarp();
-  __threadfence_block();
-  const int ep_flags = r.flags;
-  Bm25Slab out;
-  out.accb = smem_u32(acci) - 4u * uint32_t(r.slab0);      // accb + 4 * doc == &acc[doc - slab0]
-  out.thr_i = INT_MAX;
-  out.end = (ep_flags & BM25_E_END) ? 1 : 0;
-  if (out.end) return out;
-  if (ep_flags & BM25_E_ITEM_BEGIN) {
-    // the previous item ended behind a barrier: the candidate buffer is free
-    const int chain = r.chain, step = r.step;
-    const unsigned long long thr_init = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull;
-    if (tid == 0) {
-      sh.inv_scale = r.inv_scale;
-      sh.range_end = int(min(p.N, int64_t(chain % p.S + 1) * p.dps));
-    }
-    if (step == 0) {
-      if (tid == 0) { sh.cand_cnt = 0; sh.thr_key = thr_init; }
-    } else {
-      spin_until_ge(p.ws.cand_flag + chain, step);
-      const int cnt = __ldcg(p.ws.ch_cnt + chain);
-      const uint64_t* src = p.ws.ch_cand + size_t(chain) * cap;
-      for (int i = tid; i < cnt; i += BM25_CONSUMERS) cand[i] = __ldcg(src + i);
-      if (tid == 0) { sh.cand_cnt = cnt; sh.thr_key = __ldcg(p.ws.ch_thr + chain); }
+  // the previous item ended behind a barrier: the candidate buffer is free
+  if (tid == 0) {
+    sh.inv_scale = inv_scale;
+    sh.range_end = int(min(p.N, int64_t(chain % p.S + 1) * p.dps));
+  }
+  if (step == 0) {
+    if (tid == 0) { sh.cand_cnt = 0; sh.thr_key = p.nonneg ? ((uint64_t(ord32(0.0f)) << 32) | 0xffffffffull) : 0ull; }
+  } else {
+    spin_until_ge(p.ws.cand_flag + chain, step);
+    const int cnt = __ldcg(p.ws.ch_cnt + chain);
+    const uint64_t* src = p.ws.ch_cand + size_t(chain) * cap;
+    for (int i = tid; i < cnt; i += BM25_CONSUMERS) cand[i] = __ldcg(src + i);
+    if (tid == 0) { sh.cand_cnt = cnt; sh.thr_key = __ldcg(p.ws.ch_thr + chain); }
+  }
+  cbar();
+  return bm25_note_threshold(p, sh);
+}
+
+// End of an item: the chain state goes to the workspace, or (last item of the chain) its sorted top-k to the key list.
+__device__ __noinline__ void bm25_item_end(const Bm25Params& p, Bm25Shared& sh, int chain, int step, int final_step) {
+  const int tid = threadIdx.x;
+  const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
+  const int cap = p.cap;
+  int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(acci + p.slab);
+  cbar();
+  if (final_step) {
+    // ---- sorted top-k of the surviving candidates -> this chain's key list ----
+    const int ncand = min(sh.cand_cnt, cap);
+    Bm25Cands cands{cand, ncand};
+    const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acci);     // the (zeroed) slab doubles as the sort buffer
+    const int P = p.P;
+    if (tid == 0) sh.sel.nsel = 0;
+    cbar();
+    for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
+      const uint64_t key = cand[i];
+      if (key >= pivot) { const int pos = atomicAdd(&sh.sel.nsel, 1); if (pos < P) sortbuf[pos] = key; }
     }
     cbar();
+    block_sort_desc(sortbuf, P, cbar);
+    uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
+    for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
+    cbar();
+    for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
+    cbar();
+  } else {
+    const int cnt = min(sh.cand_cnt, cap);
+    uint64_t* dst = p.ws.ch_cand + size_t(chain) * cap;
+    for (int i = tid; i < cnt; i += BM25_CONSUMERS) dst[i] = cand[i];
+    if (tid == 0) { p.ws.ch_cnt[chain] = cnt; p.ws.ch_thr[chain] = sh.thr_key; }
+    __threadfence();
+    cbar();
+    if (tid == 0) st_release(p.ws.cand_flag + chain, step + 1);
   }
-  if ((ep_flags & BM25_E_SLAB) && LRAG_BM25_HOTLIST && p.nonneg) {
-    // the k-th best key was last changed behind a barrier
-    const unsigned long long thr_key = sh.thr_key;
-    const float thr_s = (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
-    const float t = thr_s / sh.inv_scale;
-    int thr_i = t >= 2147483520.f ? INT_MAX : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1;
-    out.thr_i = thr_i < 1 ? 1 : thr_i;
-  }
-  return out;
 }
 
 __global__ void __launch_bounds__(BM25_THREADS, 2)
@@ -544,14 +530,11 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
   if (tid == 0) {
     sh.cand_cnt = 0;
     sh.thr_key = 0ull;
-    sh.head = 0;
-    sh.epochs_done = 0;
     sh.hot_cnt = 0;
     for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], 1); }
     fence_barrier_init();
   }
-  for (int i = tid; i < BM25_RING; i += BM25_THREADS) { sh.ring[i] = make_int4(0, 0, 0, 0); sh.freelap[i] = 0; }
-  for (int i = tid; i < BM25_EPOCHS; i += BM25_THREADS) { sh.epoch[i].pub = 0; sh.epoch[i].closed = 0; }
+  if (tid < BM25_TABS) { sh.tab[tid].tag = 0; sh.tab[tid].arrived = BM25_WARPS; }
   // zero the slab once; every slab end leaves it zeroed again
   for (int i = tid; i < SLAB / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
@@ -639,45 +622,39 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
     mbar_wait_lazy(&sh.bempty_bar[bb], ((gcount >> 1) & 1) ^ 1);
     if (lane == 0) { sh.grp[bb].kind = 1; mbar_arrive(&sh.bfull_bar[bb]); }
   } else if (warp == BM25_CONSUMERS / 32) {
-    // ===================== emit warp: (slab, term) runs -> segment descriptors + epoch records =====================
-    int epoch = 0;          // next epoch to open
-    int widx = 0;           // next descriptor index
-    auto open_epoch = [&](int slab0, int flags, int chain, int step, float inv_scale) {
-      if (lane == 0) {
-        // the slot still belongs to epoch - BM25_EPOCHS until the consumers have left that epoch behind
-        spin_shared(&sh.epochs_done, epoch - BM25_EPOCHS + 1, true);
-        Bm25Epoch& r = sh.epoch[epoch & (BM25_EPOCHS - 1)];
-        r.slab0 = slab0; r.flags = flags; r.chain = chain; r.step = step; r.inv_scale = inv_scale;
-        __threadfence_block();
-        sts_volatile(&r.pub, epoch + 1);
-      }
+    // ===================== emit warp: (slab, term) runs -> slab tables =====================
+    int wr = 0;             // tables written
+    // next table slot, free once every consumer warp has taken its previous content
+    auto acquire = [&]() -> Bm25Tab* {
+      Bm25Tab* tb = &sh.tab[wr & (BM25_TABS - 1)];
+      if (lane == 0) { spin_shared(&tb->arrived, BM25_WARPS, false); sts_volatile(&tb->arrived, 0); }
       __syncwarp();
+      return tb;
     };
-    auto close_epoch = [&]() {
-      __threadfence_block();
+    auto publish = [&](Bm25Tab* tb, int flags, int slab0, int nruns, int nchunks, int chain, int step, float inv_scale) {
       __syncwarp();
       if (lane == 0) {
-        Bm25Epoch& r = sh.epoch[epoch & (BM25_EPOCHS - 1)];
-        r.end_idx = widx;
-        __threadfence_block();
-        sts_volatile(&r.closed, epoch + 1);
+        tb->flags = flags; tb->slab0 = slab0; tb->nruns = nruns; tb->nchunks = nchunks;
+        tb->chain = chain; tb->step = step; tb->inv_scale = inv_scale;
+        asm volatile("" ::: "memory");      // shared-memory stores of one thread are performed in order
+        sts_volatile(&tb->tag, wr / BM25_TABS + 1);
       }
-      ++epoch;
+      ++wr;
       __syncwarp();
     };
     for (uint32_t gc = 0;; ++gc) {
       const uint32_t bb = gc & 1;
       mbar_wait_lazy(&sh.bfull_bar[bb], (gc >> 1) & 1);
       const Bm25Group& G = sh.grp[bb];
-      if (G.kind != 0) { open_epoch(0, BM25_E_END, 0, 0, 0.f); close_epoch(); break; }
+      if (G.kind != 0) { publish(acquire(), BM25_F_END, 0, 0, 0, 0, 0, 0.f); break; }
       const int nt = G.nt, ns = G.ns, chain = G.chain, step = G.step;
-      if (G.first) { open_epoch(0, BM25_E_ITEM_BEGIN, chain, step, G.inv_scale); close_epoch(); }
+      if (G.first) publish(acquire(), BM25_F_ITEM_BEGIN, 0, 0, 0, chain, step, G.inv_scale);
       for (int j = 0; j < ns; ++j) {
         const int sl0 = G.b0 + j * SLAB;
         // no postings here: nothing to do, unless impacts can be negative (a slab of zero scores is ranked then)
         if (G.last_t[j] < 0 && p.nonneg) continue;
-        open_epoch(sl0, BM25_E_SLAB, chain, step, G.inv_scale);
-        for (int t0 = 0; t0 < nt; t0 += 32) {
+        for (int t0 = 0; t0 < nt || t0 == 0; t0 += 32) {
+          Bm25Tab* tb = acquire();
           const int t = t0 + lane;
           int64_t first = 0; int cnt = 0; float mult = 0.f;
           if (t < nt) {
@@ -686,164 +663,124 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
             first = G.t_start[t] + lo;
             mult = G.t_mult[t];
           }
-          // A run is cut at multiples of BM25_SEG postings counted from the 32-posting (128-byte) boundary at or below
-          // its first posting: every warp-wide load of a segment is one aligned 128-byte line.  Segments per term,
-          // exclusive prefix over the lanes:
-          const int head_skip = int(first & 31);
-          const int span = head_skip + cnt;
-          const int nseg = cnt > 0 ? (span + BM25_SEG - 1) / BM25_SEG : 0;
-          int incl = nseg;
+          // chunks of a run: BM25_SEG postings each, counted from the 32-posting (128-byte) boundary at or below its first
+          const int nch = cnt > 0 ? (int(first & 31) + cnt + BM25_SEG - 1) / BM25_SEG : 0;
+          int incl = nch;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-          const int pre = incl - nseg;
-          const int S = __shfl_sync(0xffffffffu, incl, 31);
-          for (int base = 0; base < S; base += 32) {
-            const int i = base + lane;
-            // owner term of segment i: the last lane whose prefix is <= i
-            int own = 0;
-#pragma unroll
-            for (int stp = 16; stp > 0; stp >>= 1) {
-              const int c = own + stp;
-              const int pv = __shfl_sync(0xffffffffu, pre, c & 31);
-              if (c < 32 && pv <= i) own = c;
-            }
-            const int64_t f = __shfl_sync(0xffffffffu, first, own);
-            const int sp = __shfl_sync(0xffffffffu, span, own);
-            const float m = __shfl_sync(0xffffffffu, mult, own);
-            const int pr = __shfl_sync(0xffffffffu, pre, own);
-            if (i < S) {
-              const int sj = i - pr;
-              const int64_t pos = (f & ~int64_t(31)) + int64_t(sj) * BM25_SEG;      // 32-aligned first slot
-              const int lo = sj == 0 ? int(f & 31) : 0;                             // slots [lo, hi) hold the run's postings
-              const int hi = min(BM25_SEG, sp - sj * BM25_SEG);
-              const int idx = widx + i;
-              const int slot = idx & (BM25_RING - 1), lap = idx / BM25_RING;
-              spin_shared(&sh.freelap[slot], lap, false);
-              int* r = reinterpret_cast<int*>(&sh.ring[slot]);
-              r[0] = int(uint32_t(pos)) | lo;
-              r[1] = int(uint32_t(pos >> 32) & 0xffffu) | ((hi - 1) << 16) | ((epoch & 255) << 24);
-              r[2] = __float_as_int(m);
-              __threadfence_block();
-              sts_volatile(r + 3, lap + 1);
-            }
-          }
-          widx += S;
+          tb->first_lo[lane] = int(uint32_t(first)); tb->first_hi[lane] = int(uint32_t(first >> 32));
+          tb->cnt[lane] = cnt; tb->cpre[lane] = incl - nch; tb->mult[lane] = mult;
+          const int total = __shfl_sync(0xffffffffu, incl, 31);
+          const bool last_tab = t0 + 32 >= nt;
+          publish(tb, last_tab ? BM25_F_SLAB_END : 0, sl0, min(32, max(nt - t0, 0)), total, chain, step, 0.f);
         }
-        close_epoch();
       }
-      if (G.last) { open_epoch(0, BM25_E_ITEM_END | (G.final_step ? BM25_E_FINAL : 0), chain, step, 0.f); close_epoch(); }
+      if (G.last) publish(acquire(), BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), 0, 0, 0, chain, step, 0.f);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh.bempty_bar[bb]);
     }
   } else {
     // ===================== consumers =====================
     // Scores are accumulated in fixed point (int32, per-query power-of-two scale) with shared-memory
-    // integer atomics: adds commute exactly, so the segments of a slab need no ordering between them,
+    // integer atomics: adds commute exactly, so the pieces of a slab need no ordering between them,
     // results do not depend on which warp ran first, and one ATOMS replaces a load / add / store.
-    // With non-negative impacts a doc's running score only grows, so the add that brings it to the query's
-    // running k-th best sees it happen in the atomic's return value and notes the doc in a short "hot" list: at
-    // the end of the slab only those docs are looked at (the slab is scanned in full only while there is no
-    // threshold yet, when the list overflows, or when impacts can be negative).
     const uint32_t hot_u32 = smem_u32(sh.hot), hotc_u32 = smem_u32(&sh.hot_cnt);
-    Bm25Slab cur{smem_u32(acc), INT_MAX, 0};
-    int my_epoch = -1;        // epoch this warp is in
+    const uint32_t acc_u32 = smem_u32(acc);
+    int thr_i = INT_MAX;      // an add whose doc reaches this fixed-point score notes the doc
+    int thr_slab = INT_MAX;   // thr_i at the start of the slab (a thread that saw the hot list overflow stops noting)
 
     // one posting: add; returns the doc's running score
-    auto add_posting = [&](int doc, float imp, float ms) -> int {
+    auto add_posting = [&](uint32_t accb, int doc, float imp, float ms) -> int {
       const int vi = __float2int_rn(imp * ms);
-      return atoms_add_s32(cur.accb + 4u * uint32_t(doc), vi) + vi;
+      return atoms_add_s32(accb + 4u * uint32_t(doc), vi) + vi;
     };
     // note a doc whose running score reached the threshold (rare)
     auto note_hot = [&](int doc) {
       uint32_t at;
       asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(hotc_u32) : "memory");
       if (at < uint32_t(BM25_HOT)) asm volatile("st.shared.s32 [%0], %1;" ::"r"(hot_u32 + 4u * at), "r"(doc) : "memory");
-      else cur.thr_i = INT_MAX;                                // overflow: the slab will be scanned in full
+      else thr_i = INT_MAX;                                    // overflow: the slab will be scanned in full
     };
 
-    // the claim of the next descriptor is issued one segment ahead: its latency hides behind the adds
-    int next_idx = 0;
-    if (lane == 0) next_idx = atomicAdd(&sh.head, 1);
-    for (;;) {
-      const int idx = __shfl_sync(0xffffffffu, next_idx, 0);
-      const int slot = idx & (BM25_RING - 1), lap = idx / BM25_RING;
-      const int* rw = reinterpret_cast<const int*>(&sh.ring[slot]);
-      // ---- until the descriptor is published, follow the epochs that close in front of it; then the epochs up to its own.
-      //      No posting is loaded before the warp is in the descriptor's epoch: the loop below keeps its sixteen loaded
-      //      values in registers only because no call lies between the loads and the adds. ----
-      int4 de = make_int4(0, 0, 0, 0);
-      bool got = false;
-      long long t0 = 0;
-      for (;;) {
-        if (!got && lds_volatile(rw + 3) == lap + 1) {
-          __threadfence_block();
-          asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(de.x), "=r"(de.y), "=r"(de.z), "=r"(de.w)
-                       : "r"(smem_u32(&sh.ring[slot])) : "memory");
-          __syncwarp();
-          if (lane == 0) {
-            sts_volatile(&sh.freelap[slot], lap + 1);
-            if (LRAG_BM25_CLAIM_AHEAD) next_idx = atomicAdd(&sh.head, 1);
+    for (int rd = 0;; ++rd) {
+      // ---- next slab table ----
+      Bm25Tab* tb = &sh.tab[rd & (BM25_TABS - 1)];
+      {
+        const int want = rd / BM25_TABS + 1;
+        long long t0 = 0;
+        while (lds_volatile(&tb->tag) != want) {
+          __nanosleep(20);
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 20000000000LL) {
+            printf("lrag: bm25 table wait timed out (block %d warp %d table %d)\n", blockIdx.x, warp, rd);
+            __trap();
           }
-          got = true;
-        }
-        bool walk;
-        if (got) {
-          walk = ((((de.y >> 24) & 0xff) - my_epoch) & 255) != 0;
-          if (!walk) break;
-        } else {
-          walk = my_epoch < 0;
-          if (!walk) {
-            const Bm25Epoch& r = sh.epoch[my_epoch & (BM25_EPOCHS - 1)];
-            if (lds_volatile(&r.closed) == my_epoch + 1) walk = idx >= lds_volatile(&r.end_idx);
-          }
-        }
-        if (walk) {
-          if (my_epoch >= 0) bm25_end_epoch(p, sh, my_epoch);
-          ++my_epoch;
-          cur = bm25_begin_epoch(p, sh, my_epoch);
-          if (cur.end) break;
-          t0 = 0;
-          continue;
-        }
-        __nanosleep(32);
-        if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > 20000000000LL) {
-          printf("lrag: bm25 descriptor wait timed out (block %d warp %d idx %d epoch %d)\n", blockIdx.x, warp, idx, my_epoch);
-          __trap();
         }
       }
-      if (cur.end) break;
-      // ---- the segment: 8 coalesced (doc, impact) loads per lane, then the adds ----
-      const int64_t base = int64_t(uint32_t(de.x) & ~31u) | (int64_t(de.y & 0xffff) << 32);
-      const int lo = de.x & 31, hi = ((de.y >> 16) & 0xff) + 1;
-      const float ms = __int_as_float(de.z);                       // term multiplicity x scale
-      const int32_t* pid = p.doc_id + base + lane;
-      const float* pim = p.impact + base + lane;
-      int d[BM25_SEG_PER_LANE]; float v[BM25_SEG_PER_LANE];
-      if (lo == 0 && hi == BM25_SEG) {
+      asm volatile("" ::: "memory");            // shared-memory loads of one thread are performed in order
+      int4 h0, h1;
+      asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h0.x), "=r"(h0.y), "=r"(h0.z), "=r"(h0.w)
+                   : "r"(smem_u32(&tb->flags)) : "memory");
+      asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h1.x), "=r"(h1.y), "=r"(h1.z), "=r"(h1.w)
+                   : "r"(smem_u32(&tb->chain)) : "memory");
+      const int flags = h0.x, slab0 = h0.y, nruns = h0.z, nchunks = h0.w;
+      // this lane's run
+      uint32_t r_lo = 0; int r_hi = 0, r_cnt = 0, r_cpre = INT_MAX; float r_mult = 0.f;
+      if (lane < nruns) {
+        r_lo = uint32_t(lds_volatile(&tb->first_lo[lane])); r_hi = lds_volatile(&tb->first_hi[lane]);
+        r_cnt = lds_volatile(&tb->cnt[lane]); r_cpre = lds_volatile(&tb->cpre[lane]);
+        r_mult = __int_as_float(lds_volatile(reinterpret_cast<const int*>(&tb->mult[lane])));
+      }
+      __syncwarp();
+      if (lane == 0) atomicAdd(&tb->arrived, 1);           // the table is in registers: its slot may be rewritten
+      if (flags & BM25_F_ITEM_BEGIN) thr_slab = thr_i = bm25_item_begin(p, sh, h1.x, h1.y, __int_as_float(h1.z));
+      // ---- this warp's chunks of the slab: c = warp, warp + 16, ...; 8 coalesced (doc, impact) loads per lane, then the adds ----
+      const uint32_t accb = acc_u32 - 4u * uint32_t(slab0);        // accb + 4 * doc == &acc[doc - slab0]
+      for (int c = warp; c < nchunks; c += BM25_WARPS) {
+        // the run that holds chunk c: the last one whose chunk prefix is <= c
+        const int t = __popc(__ballot_sync(0xffffffffu, r_cpre <= c)) - 1;
+        const uint32_t f_lo = __shfl_sync(0xffffffffu, r_lo, t);
+        const int f_hi = __shfl_sync(0xffffffffu, r_hi, t);
+        const int cnt = __shfl_sync(0xffffffffu, r_cnt, t);
+        const int j = c - __shfl_sync(0xffffffffu, r_cpre, t);
+        const float ms = __shfl_sync(0xffffffffu, r_mult, t);      // term multiplicity x scale
+        const int64_t first = int64_t(f_lo) | (int64_t(f_hi) << 32);
+        const int64_t base = (first & ~int64_t(31)) + int64_t(j) * BM25_SEG;
+        const int lo = j == 0 ? int(f_lo & 31) : 0;                // slots [lo, hi) of the chunk belong to the run
+        const int64_t left = first + cnt - base;
+        const int hi = left < BM25_SEG ? int(left) : BM25_SEG;
+        const int32_t* pid = p.doc_id + base + lane;
+        const float* pim = p.impact + base + lane;
+        int d[BM25_SEG_PER_LANE]; float v[BM25_SEG_PER_LANE];
+        if (lo == 0 && hi == BM25_SEG) {
 #pragma unroll
-        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
-        int tot[BM25_SEG_PER_LANE];
-        int top = INT_MIN;
+          for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
+          int tot[BM25_SEG_PER_LANE];
+          int top = INT_MIN;
 #pragma unroll
-        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { tot[u] = add_posting(d[u], v[u], ms); top = max(top, tot[u]); }
-        if (top >= cur.thr_i) {                                  // one branch per eight postings; taken rarely
+          for (int u = 0; u < BM25_SEG_PER_LANE; ++u) { tot[u] = add_posting(accb, d[u], v[u], ms); top = max(top, tot[u]); }
+          if (top >= thr_i) {                                      // one branch per eight postings; taken rarely
+#pragma unroll
+            for (int u = 0; u < BM25_SEG_PER_LANE; ++u)
+              if (tot[u] >= thr_i) note_hot(d[u]);
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < BM25_SEG_PER_LANE; ++u) {
+            d[u] = -1; v[u] = 0.f;
+            const int sl = lane + 32 * u;
+            if (sl >= lo && sl < hi) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
+          }
 #pragma unroll
           for (int u = 0; u < BM25_SEG_PER_LANE; ++u)
-            if (tot[u] >= cur.thr_i) note_hot(d[u]);
+            if (d[u] >= 0 && add_posting(accb, d[u], v[u], ms) >= thr_i) note_hot(d[u]);
         }
-      } else {
-#pragma unroll
-        for (int u = 0; u < BM25_SEG_PER_LANE; ++u) {
-          d[u] = -1; v[u] = 0.f;
-          const int sl = lane + 32 * u;
-          if (sl >= lo && sl < hi) { d[u] = ldg_stream_s32(pid + 32 * u); v[u] = ldg_stream_f32(pim + 32 * u); }
-        }
-#pragma unroll
-        for (int u = 0; u < BM25_SEG_PER_LANE; ++u)
-          if (d[u] >= 0 && add_posting(d[u], v[u], ms) >= cur.thr_i) note_hot(d[u]);
       }
-      if (!LRAG_BM25_CLAIM_AHEAD && lane == 0) next_idx = atomicAdd(&sh.head, 1);
+      // ---- markers: every consumer warp sees the same ones ----
+      if (flags & BM25_F_SLAB_END) thr_slab = bm25_slab_end(p, sh, slab0, thr_slab);
+      if (flags & BM25_F_ITEM_END) bm25_item_end(p, sh, h1.x, h1.y, flags & BM25_F_FINAL);
+      if (flags & BM25_F_END) break;
+      thr_i = thr_slab;
     }
   }
 }

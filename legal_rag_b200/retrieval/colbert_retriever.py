@@ -37,7 +37,8 @@ def build_token_store(cfg, chunks: Sequence[LawChunk], encoder=None) -> Path:
     unit 128-d token vectors, pad to a common length (32, 64, 128 or 256 rows: lengths that tile the 256-row
     block of the batched full-corpus scan) and save bf16 bits + lengths."""
     rcfg = cfg.retrieval
-    enc = encoder or encoders.make_token_encoder(str(rcfg.colbert_model_name), "cpu")
+    enc = encoder or encoders.make_token_encoder(str(rcfg.colbert_model_name), "cpu",
+                                                 doc_maxlen=int(getattr(rcfg, "colbert_doc_maxlen", 220)))
     mats = [np.asarray(enc.encode_doc((c.text or "").strip()), dtype=np.float32)[: int(getattr(rcfg, "colbert_doc_maxlen", 220))]
             for c in chunks]
     longest = max(m.shape[0] for m in mats)
@@ -82,7 +83,8 @@ class ColBERTRetriever:
         self._load_meta_and_collection()
         self._load_token_store()
         if self._encoder is None:
-            self._encoder = encoders.make_token_encoder(str(self.model_name), self.device)
+            self._encoder = encoders.make_token_encoder(str(self.model_name), self.device, query_maxlen=QUERY_MAXLEN,
+                                                        doc_maxlen=int(getattr(rcfg, "colbert_doc_maxlen", 220)))
 
     @classmethod
     def from_config(cls, cfg) -> "ColBERTRetriever":
@@ -127,6 +129,10 @@ class ColBERTRetriever:
         self._tokens, self._doclen, self._store_mtime = toks, doclen, mtime
 
     def _encode_queries(self, queries: Sequence[str]) -> torch.Tensor:
+        if hasattr(self._encoder, "encode_queries_device"):
+            # checkpoint-backed encoder on the index's device: text -> kernel operand without a host round trip
+            Q = self._encoder.encode_queries_device(list(queries))[:, :QUERY_MAXLEN]
+            return Q.to(self.device).to(torch.bfloat16).contiguous()
         mats = [np.asarray(self._encoder.encode_query(q), dtype=np.float32)[:QUERY_MAXLEN] for q in queries]
         Lq = max(m.shape[0] for m in mats)
         Q = np.zeros((len(mats), Lq, DIM), dtype=np.float32)     # zero rows add max_j <0, d_j> = 0 to every doc

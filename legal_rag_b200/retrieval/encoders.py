@@ -10,6 +10,7 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
+_warned_no_jieba = False
 _TOKEN_RE = re.compile(r"[A-Za-z0-9]+(?:'[A-Za-z0-9]+)?|[一-鿿]|\s+|[^\sA-Za-z0-9一-鿿]")
 
 
@@ -26,6 +27,13 @@ def default_query_tokenizer() -> Callable[[str], List[str]]:
         import jieba
         return lambda q: list(jieba.cut(q))
     except ImportError:
+        global _warned_no_jieba
+        if not _warned_no_jieba:
+            _warned_no_jieba = True
+            import logging
+            logging.getLogger(__name__).warning(
+                "jieba is not installed: BM25 queries are split by a regex (words / whitespace runs / punctuation / single CJK "
+                "characters); Chinese queries tokenise differently from the reference (bm25_retriever.py:73)")
         return lambda q: _TOKEN_RE.findall(q)
 
 
@@ -118,6 +126,127 @@ class TransformersBgeEncoder:
         return v[0] if single else v
 
 
+class TransformersColbertEncoder:
+    """ColBERT checkpoint directory -> unit 128-d token vectors on the index's device, for installs that
+    have the checkpoint on disk and `transformers` but not colbert-ai.  It restates what the reference's Searcher / Indexer do
+    with the checkpoint (colbert_retriever.py:119-152, builders/colbert_builder.py:109-134) [upstream colbert-ai 0.2.x,
+    colbert/modeling/{hf_colbert,checkpoint,tokenization}]: BERT encoder + a bias-free linear layer hidden -> dim; every
+    text is prefixed with ". " and the token after [CLS] is overwritten by the marker [unused0] (queries) / [unused1]
+    (documents); queries are padded to `query_maxlen` with [MASK] tokens that are not attended to but whose output vectors
+    are kept (query augmentation); document tokens that are padding or punctuation are dropped (mask_punctuation); every
+    kept vector is L2-normalised.  The transformer forward is library code (HF transformers); the vectors go straight to
+    the MaxSim kernels as device tensors (`encode_queries_device`)."""
+
+    def __init__(self, model_path: str, device="cpu", query_maxlen: Optional[int] = None, doc_maxlen: Optional[int] = None,
+                 use_fp16: Optional[bool] = None):
+        import json
+        import os
+        import string
+        import torch
+        from transformers import AutoModel, AutoTokenizer
+        self.device = torch.device(device)
+        meta = {}
+        meta_path = os.path.join(model_path, "artifact.metadata")           # written by colbert's checkpoint saver
+        if os.path.exists(meta_path):
+            with open(meta_path) as f:
+                meta = json.load(f)
+        self.query_maxlen = int(query_maxlen or meta.get("query_maxlen", 32))
+        self.doc_maxlen = int(doc_maxlen or meta.get("doc_maxlen", 220))
+        self.attend_to_mask_tokens = bool(meta.get("attend_to_mask_tokens", False))
+        self.mask_punctuation = bool(meta.get("mask_punctuation", True))
+        self.tokenizer = AutoTokenizer.from_pretrained(model_path, local_files_only=True)
+        bert = AutoModel.from_pretrained(model_path, local_files_only=True)
+        weight = self._linear_weight(model_path)
+        if weight.shape[1] != bert.config.hidden_size:
+            raise RuntimeError(f"ColBERT checkpoint {model_path}: linear.weight {tuple(weight.shape)} does not match hidden size "
+                               f"{bert.config.hidden_size}")
+        if use_fp16 is None:
+            use_fp16 = self.device.type == "cuda"
+        self.model = (bert.half() if use_fp16 else bert.float()).to(self.device).eval()
+        self.linear = weight.to(self.device).to(torch.float16 if use_fp16 else torch.float32)     # [dim, hidden], no bias
+        self.dim = int(weight.shape[0])
+        tok = self.tokenizer
+        self.q_marker = tok.convert_tokens_to_ids("[unused0]")
+        self.d_marker = tok.convert_tokens_to_ids("[unused1]")
+        self.skip_ids = set()
+        if self.mask_punctuation:
+            for sym in string.punctuation:
+                ids = tok.encode(sym, add_special_tokens=False)
+                if ids:
+                    self.skip_ids.add(int(ids[0]))
+
+    @staticmethod
+    def _linear_weight(model_path: str):
+        """`linear.weight` of the checkpoint (HF_ColBERT keeps it next to the `bert.*` tensors)."""
+        import os
+        import torch
+        st = os.path.join(model_path, "model.safetensors")
+        if os.path.exists(st):
+            from safetensors import safe_open
+            with safe_open(st, framework="pt") as f:
+                for name in ("linear.weight", "colbert.linear.weight"):
+                    if name in f.keys():
+                        return f.get_tensor(name).float()
+        pt = os.path.join(model_path, "pytorch_model.bin")
+        if os.path.exists(pt):
+            sd = torch.load(pt, map_location="cpu", weights_only=True)
+            for name in ("linear.weight", "colbert.linear.weight"):
+                if name in sd:
+                    return sd[name].float()
+        raise RuntimeError(f"ColBERT checkpoint {model_path}: no linear.weight tensor (not a ColBERT checkpoint directory?)")
+
+    def _forward(self, ids, mask):
+        import torch
+        with torch.no_grad():
+            h = self.model(input_ids=ids, attention_mask=mask).last_hidden_state
+            return h @ self.linear.t()
+
+    def encode_queries_device(self, queries: Sequence[str]):
+        """-> float32 [nq, query_maxlen, dim] on the device; every row is a unit vector ([MASK] rows included)."""
+        import torch
+        tok = self.tokenizer
+        obj = tok([". " + q for q in queries], padding="max_length", truncation=True, max_length=self.query_maxlen, return_tensors="pt")
+        ids, mask = obj["input_ids"], obj["attention_mask"]
+        ids[:, 1] = self.q_marker
+        ids[ids == tok.pad_token_id] = tok.mask_token_id
+        if self.attend_to_mask_tokens:
+            mask[ids == tok.mask_token_id] = 1
+        Q = self._forward(ids.to(self.device), mask.to(self.device)).float()
+        return torch.nn.functional.normalize(Q, p=2, dim=2)
+
+    def encode_docs_device(self, docs: Sequence[str], batch_size: int = 32):
+        """-> (float32 [n, Lmax, dim] on the device, zero rows past each doc's length; int32 [n] lengths).  Kept tokens are
+        packed to the front in their original order, like the Indexer's `D[mask]`."""
+        import torch
+        tok = self.tokenizer
+        mats, lens = [], []
+        for i in range(0, len(docs), batch_size):
+            obj = tok([". " + d for d in docs[i:i + batch_size]], padding="longest", truncation="longest_first", max_length=self.doc_maxlen,
+                      return_tensors="pt")
+            ids, mask = obj["input_ids"], obj["attention_mask"]
+            ids[:, 1] = self.d_marker
+            keep = torch.tensor([[(int(x) not in self.skip_ids) and (int(x) != tok.pad_token_id) for x in row] for row in ids.tolist()])
+            D = self._forward(ids.to(self.device), mask.to(self.device)).float()
+            D = torch.nn.functional.normalize(D * keep.to(self.device).unsqueeze(2), p=2, dim=2)
+            for r in range(D.shape[0]):
+                rows = D[r][keep[r].to(self.device)]
+                mats.append(rows)
+                lens.append(rows.shape[0])
+        Lmax = max(lens) if lens else 0
+        out = torch.zeros((len(mats), Lmax, self.dim), dtype=torch.float32, device=self.device)
+        for i, m in enumerate(mats):
+            out[i, : m.shape[0]] = m
+        return out, torch.tensor(lens, dtype=torch.int32, device=self.device)
+
+    # the numpy interface the token-store builder and ColBERTRetriever use
+    def encode_query(self, text: str) -> np.ndarray:
+        return self.encode_queries_device([text])[0].cpu().numpy()
+
+    def encode_doc(self, text: str) -> np.ndarray:
+        D, n = self.encode_docs_device([text])
+        return D[0, : int(n[0])].cpu().numpy()
+
+
 _dense_encoder_factory: Optional[Callable] = None
 _token_encoder_factory: Optional[Callable] = None
 
@@ -152,9 +281,14 @@ def make_dense_encoder(model_name: str, device):
                      use_fp16=torch.cuda.is_available(), device=device)      # vector_store.py:70-75
 
 
-def make_token_encoder(model_name: str, device):
+def make_token_encoder(model_name: str, device, query_maxlen: Optional[int] = None, doc_maxlen: Optional[int] = None):
+    """A registered factory wins; else a ColBERT checkpoint DIRECTORY is loaded through HF transformers on the index's
+    device (the reference hands the same `colbert_model_name` to colbert's Searcher, colbert_retriever.py:135-136)."""
     if _token_encoder_factory is not None:
         return _token_encoder_factory(model_name, device)
+    import os
+    if os.path.isdir(str(model_name)):
+        return TransformersColbertEncoder(str(model_name), device, query_maxlen=query_maxlen, doc_maxlen=doc_maxlen)
     raise RuntimeError(
-        "no ColBERT token encoder registered (legal_rag_b200.retrieval.encoders.register_token_encoder); "
-        "loading colbert-ai checkpoints is outside the accelerated path")
+        f"no ColBERT token encoder: {model_name!r} is not a local checkpoint directory (there is no network access to a model "
+        "hub here) and no encoder was registered (legal_rag_b200.retrieval.encoders.register_token_encoder)")

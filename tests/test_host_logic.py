@@ -330,3 +330,64 @@ def test_transformers_bge_encoder_matches_flagmodel_semantics(tmp_path):
     np.testing.assert_allclose(q, enc.encode([encoders.BGE_QUERY_INSTRUCTION + "goods"]), atol=1e-6)
     assert not np.allclose(q[0], v[1], atol=1e-3)                       # the instruction changes the query vector
     assert enc.encode("goods").shape == (32,)                            # a bare string gives one vector (graph_retriever.py:177)
+
+
+def test_transformers_colbert_encoder_restates_the_checkpoint_pipeline(tmp_path):
+    """encoders.TransformersColbertEncoder on a tiny random-init ColBERT-style checkpoint saved to disk (no network): ". " prefix,
+    [unused0] / [unused1] markers, [MASK] augmentation to query_maxlen with the mask tokens not attended to, punctuation and
+    padding dropped from documents, unit-norm rows -- what colbert's Checkpoint does with the directory the reference passes
+    to Searcher / Indexer (colbert_retriever.py:135-136, builders/colbert_builder.py:123-132)."""
+    import json
+    import torch
+    from safetensors.torch import load_file, save_file
+    from transformers import BertConfig, BertModel, BertTokenizerFast
+    vocab = (["[PAD]", "[unused0]", "[unused1]", "[UNK]", "[CLS]", "[SEP]", "[MASK]", ".", ",", "?", "!"]
+             + ["buyer", "seller", "goods", "contract", "sale", "of", "the", "a"])
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    (d / "vocab.txt").write_text("\n".join(vocab), encoding="utf-8")
+    BertTokenizerFast(vocab_file=str(d / "vocab.txt")).save_pretrained(d)
+    torch.manual_seed(1)
+    bert = BertModel(BertConfig(vocab_size=len(vocab), hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
+                                max_position_embeddings=64))
+    bert.eval()
+    bert.save_pretrained(d)
+    # an HF_ColBERT checkpoint keeps `linear.weight` next to the bert.* tensors
+    sd = {"bert." + k: v.contiguous() for k, v in load_file(d / "model.safetensors").items()}
+    W = torch.randn(16, 32)
+    sd["linear.weight"] = W
+    save_file(sd, d / "model.safetensors", metadata={"format": "pt"})
+    (d / "artifact.metadata").write_text(json.dumps({"query_maxlen": 8, "doc_maxlen": 12, "dim": 16}))
+
+    enc = encoders.make_token_encoder(str(d), "cpu")
+    assert isinstance(enc, encoders.TransformersColbertEncoder) and enc.dim == 16 and enc.query_maxlen == 8
+    tok = enc.tokenizer
+    # ---- query: 8 rows whatever the text length, all unit vectors ----
+    q = enc.encode_query("sale of goods")
+    assert q.shape == (8, 16) and q.dtype == np.float32
+    np.testing.assert_allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-5)
+    ids = tok([". sale of goods"], padding="max_length", truncation=True, max_length=8, return_tensors="pt")
+    ii, mm = ids["input_ids"].clone(), ids["attention_mask"]
+    assert ii[0, 1].item() == tok.convert_tokens_to_ids(".")          # the ". " prefix is what the marker overwrites
+    ii[:, 1] = tok.convert_tokens_to_ids("[unused0]")
+    ii[ii == tok.pad_token_id] = tok.mask_token_id
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(bert(input_ids=ii, attention_mask=mm).last_hidden_state @ W.t(), dim=2)[0].numpy()
+    np.testing.assert_allclose(q, ref, atol=1e-5)
+    # ---- document: punctuation and padding rows are gone, the rest are unit vectors in order ----
+    doc = "the buyer, the seller!"
+    dv = enc.encode_doc(doc)
+    ids = tok([". " + doc], return_tensors="pt")["input_ids"]
+    punct = {tok.convert_tokens_to_ids(x) for x in [".", ",", "?", "!"]}
+    ids[:, 1] = tok.convert_tokens_to_ids("[unused1]")
+    keep = [i for i, t in enumerate(ids[0].tolist()) if t not in punct]
+    assert dv.shape == (len(keep), 16) and len(keep) == ids.shape[1] - 2         # "," and "!" dropped; [CLS] [D] [SEP] kept
+    with torch.no_grad():
+        ref = torch.nn.functional.normalize(bert(input_ids=ids).last_hidden_state @ W.t(), dim=2)[0].numpy()[keep]
+    np.testing.assert_allclose(dv, ref, atol=1e-5)
+    # a batch pads to the longest document and reports the lengths
+    D, n = enc.encode_docs_device([doc, "goods"])
+    assert D.shape[0] == 2 and int(n[0]) == len(keep) and int(n[1]) == 4 and float(D[1, 4:].abs().sum()) == 0.0
+    # not a directory, nothing registered: the channel cannot be built, and says why
+    with pytest.raises(RuntimeError, match="not a local checkpoint directory"):
+        encoders.make_token_encoder("colbert-ir/colbertv2.0", "cpu")
