@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md).
+"""Benchmark of the hybrid-retrieval hot path (contract: see the task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dense|maxsim|maxsim_scan|bm25|hybrid|ucc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload hybrid|dense|maxsim|maxsim_scan|bm25|ucc]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
 
-One "step" = one pass of the hot path over one batch of synthetic queries.  At N=1 the default
-workload is BASELINE.json configs[1] (dense flat-IP top-100, 10M x 1024 bf16, 4096 queries).  With N
-ranks every rank owns its own 10M-row shard (the corpus grows to N x 10M: weak scaling), computes its
-local top-k and the lists are merged after one NCCL all-gather.  The default run then adds a "hybrid" object to
-the same line: every rank's 1/8 shard of configs[4] (12.5M x 768 dense rows + BM25 + ColBERT rerank + fusion)
-through the sharded hybrid pipeline, measured the same way (--no-hybrid-block skips it).
-Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of synthetic queries.  The default workload is the metric's own:
+BASELINE.json configs[4], the full hybrid step (dense 768-d flat-IP + BM25 + ColBERT MaxSim rerank + weighted fusion, k = 100,
+4096 queries).  configs[4] is 100M documents over 8 GPUs and does not fit one: every rank owns 1/8 of it (12.5M docs: weak
+scaling, 8 ranks hold exactly configs[4]), computes local top-k lists, and the lists meet in one NCCL all-gather + merge per
+step.  The JSON line (rank 0) carries, besides the contract's keys:
+  roofline        the LONGEST stage of the step against its bound, and `stages`: every kernel family of the step with its own
+                  algorithmic work, device time (CUDA events on the launching stream) and fraction of the measured peak
+  parity_check    32 sampled queries recomputed with plain torch on every rank and merged (bench_parity.py): ids at N GPUs
+  strong          (N > 1) the same per-GPU shard split over the N ranks: ms/step, speed-up, what the rest of the step costs
+  kernels         (N = 1) short runs of the other configs (configs[1] dense, configs[2] MaxSim, configs[3] BM25, full-scan MaxSim,
+                  top-k select shapes), each with its roofline, so that every kernel family has a driver-run number
+  api             (N = 1) the reference's class API on configs[0]'s corpus: HybridRetriever.search / search_batch
+  cpu_baseline    the oracle port of the reference's path on the host cores, bounded sample
 """
 from __future__ import annotations
 
@@ -332,10 +338,9 @@ class HybridWorkload:
     12.5M BM25 docs of mean length 24, 125k x 128 x 128 token rows), so 8 ranks hold exactly configs[4]."""
     name = "hybrid_top100"
     dtype = "bf16"
-    dominant = "dense_scan"
 
-    def __init__(self, args, rank, world, device):
-        self.N, self.d, self.V = args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
+    def __init__(self, args, rank, world, device, n_docs=None):
+        self.N, self.d, self.V = n_docs or args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
         self.nq, self.k, self.kc = args.nq or 4096, args.k, (getattr(args, "kc", 0) or args.k)
         self.colbert_mode = getattr(args, "colbert_mode", "rerank")
         # rerank: configs[4]'s 1M-doc token store (ids aliased onto it); scan: one token row per document of the shard
@@ -350,13 +355,16 @@ class HybridWorkload:
                             + ", weighted_sum 0.6/0.4/0.35",
                 "corpus_docs_total": self.N * self.world, "postings": getattr(self, "nnz", None),
                 "token_rows": "global id mod total token rows (synthetic aliasing of the id space onto the token store, SURVEY 8d C5)",
-                "parallelism": (f"doc-sharded x{self.world}: per channel local top-k + NCCL all-gather + merge, MaxSim by row owner + NCCL max-reduce, "
-                                f"replicated fusion") if self.world > 1 else "single GPU",
-                "l2": f"dense shard {self.N * self.d * 2 / 1e9:.1f} GB >> 126 MB L2",
+                "parallelism": (f"doc-sharded x{self.world}: per channel local top-k, ONE packed NCCL all-gather, merge kernels that read the "
+                                f"gathered buffers in place, MaxSim by row owner + NCCL max-reduce, replicated fusion") if self.world > 1 else "single GPU",
+                "l2": f"dense shard {self.N * self.d * 2 / 1e9:.1f} GB, postings {getattr(self, 'nnz', 0) * 8 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
                 "stages_ms": getattr(self, "stages_ms", None),
-                "value_definition": "value = n_gpus * batch_queries * steps / time (every rank answers the whole batch against its shard)"}
+                "value_definition": "weak scaling: every rank answers the whole batch against its own 1/8 shard of configs[4]; "
+                                    "value = n_gpus * batch_queries * steps / time (shard-level query scans per second); "
+                                    "global_queries_per_s = batch_queries * steps / time is the rate at which the n_gpus-shard corpus answers queries"}
 
     def setup(self):
+        import numpy as np
         import torch
         from legal_rag_b200 import engine, synth
         self.torch, self.engine = torch, engine
@@ -372,10 +380,16 @@ class HybridWorkload:
         self.q_indptr, self.q_term, self.mx = synth.bm25_synthetic_queries(self.nq, self.V, 11, self.device)
         self.Qtok = synth.unit_tokens_bf16(self.nq, self.Lq, 128, 7, self.device)
         self.host = [t.cpu().pin_memory() for t in (self.Qd, self.q_indptr, self.q_term, self.Qtok)]
+        # exact algorithmic posting bytes of this shard's BM25 stage: 8 B x sum over queries of df over the query's distinct terms
+        df = st["df"].cpu().numpy()
+        qi, qt = self.q_indptr.cpu().numpy(), self.q_term.cpu().numpy()
+        self.alg_postings = int(sum(int(df[np.unique(qt[qi[j]:qi[j + 1]])].sum()) for j in range(self.nq)))
+        self.cand_owned = None
         self._stage_times()
 
     def _stage_times(self):
-        """Per-stage device times of one step (outside the timed region), reported in config.stages_ms."""
+        """Per-stage device times of one step, run stage by stage with a synchronising event after each (outside the timed
+        region), reported in config.stages_ms.  Also counts the MaxSim candidates this rank scores."""
         torch, eng, sh = self.torch, self.engine, self.shard
         ev = lambda: torch.cuda.Event(enable_timing=True)
         for _ in range(2):
@@ -389,6 +403,7 @@ class HybridWorkload:
                 _, gid = eng.fuse_topk(d, b, None, k=2 * self.kc, method="weighted_sum")
                 rows = torch.where(gid >= 0, gid % sh.tok_rows_total, gid) - sh.tok_row_base
                 own = (gid >= 0) & (rows >= 0) & (rows < sh.tokens.shape[0])
+                self.cand_owned = int(own.sum())
                 eng.maxsim_scores(sh.tokens, None, self.Qtok, torch.where(own, rows, torch.full_like(rows, -1)))
             else:
                 eng.allgather_merge(*eng.maxsim_scan_topk(sh.tokens, None, self.Qtok, self.kc, id_base=sh.id_base), self.kc)
@@ -413,19 +428,97 @@ class HybridWorkload:
     def units_per_step(self):
         return self.nq * self.world
 
-    def roofline(self, kernel_ms, peaks):
+    def stage_rooflines(self, by_tag, peaks):
+        """One entry per kernel family of the step: algorithmic work per step, device time per step (summed over the family's
+        launches), achieved rate and fraction of the measured peak that bounds it."""
+        out = []
+        def entry(kernel, tag, bound, work, unit_div, unit, peak, alg, **extra):
+            ms = by_tag.get(tag, 0.0)
+            if ms <= 0:
+                return
+            ach = work / (ms * 1e-3) / unit_div
+            out.append(dict({"kernel": kernel, "bound": bound, "kernel_ms": ms, "achieved": ach, "peak": peak, "unit": unit,
+                             "frac": ach / peak, "algorithmic": alg}, **extra))
         flops = 2.0 * self.nq * self.N * self.d
-        ach = flops / (kernel_ms * 1e-3) / 1e12
-        return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "traffic": None, "kernel": "dense_scan_kernel (dominant stage of the hybrid step)", "kernel_ms": kernel_ms,
-                "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per step", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)"}
+        entry("dense_scan_kernel", "dense_scan", "tensor", flops, 1e12, "TFLOP/s", peaks["bf16_tflops"], f"2*nq*N*d = {flops:.3e} FLOP",
+              peak_burst=peaks["bf16_tflops_burst"])
+        pbytes = 8.0 * self.alg_postings
+        entry("bm25_scan_kernel", "bm25_scan", "hbm", pbytes, 1e9, "GB/s", peaks["hbm_gbs"],
+              f"8 B x sum_q sum_(distinct t in q) df(t) = {pbytes:.4e} B (served from L2 after the first touch: a posting-throughput "
+              f"figure quoted against the HBM copy peak, see DESIGN 4.2)",
+              traffic=measured_traffic("bm25_scan_kernel", N=self.N, V=self.V, nq=self.nq, k=self.kc, mean_len=24.0))
+        if self.colbert_mode == "rerank" and self.cand_owned:
+            mbytes = float(self.cand_owned) * self.Ld * 128 * 2
+            entry("maxsim_kernel", "maxsim", "hbm", mbytes, 1e9, "GB/s", peaks["hbm_gbs"],
+                  f"owned candidates x Ld x dim x 2 = {self.cand_owned} x {self.Ld} x 128 x 2 = {mbytes:.3e} B")
+        else:
+            sflops = 2.0 * self.nq * self.Lq * 128 * self.Nd_tok * self.Ld
+            entry("maxsim_scan_kernel", "maxsim_scan", "tensor", sflops, 1e12, "TFLOP/s", peaks["bf16_tflops"], f"2*nq*Lq*dim*Nd*Ld = {sflops:.3e} FLOP")
+        fbytes = float(self.nq) * (2 * self.kc * 12 + 2 * self.kc * 12) + float(self.nq) * (3 * self.kc * 12 + self.k * 12)
+        entry("fuse_kernel", "fuse", "hbm", fbytes, 1e9, "GB/s", peaks["hbm_gbs"],
+              f"two launches: candidate union (2 lists in, 2 kc out) + final fusion (3 lists in, k out) = {fbytes:.3e} B; latency-bound at "
+              f"this size (DESIGN 4.4)")
+        sbytes = float(self.nq) * 2 * self.kc * (4 + 8 + 12)
+        entry("topk_select_kernel", "select", "hbm", sbytes, 1e9, "GB/s", peaks["hbm_gbs"],
+              f"MaxSim scores + candidate ids in, kc hits out = {sbytes:.3e} B; latency-bound at this size")
+        return out
+
+    def roofline(self, by_tag, peaks):
+        stages = self.stage_rooflines(by_tag, peaks)
+        top = max(stages, key=lambda e: e["kernel_ms"])
+        roof = dict(top)
+        roof.setdefault("traffic", None)
+        roof["kernel"] = top["kernel"] + " (longest stage of the hybrid step)"
+        roof["peak_source"] = peaks["source"] + (" (copy bandwidth)" if top["bound"] == "hbm" else " (sustained cuBLAS bf16)")
+        roof["stages"] = stages
+        return roof
+
+    # ---- self-check: 32 sampled queries through plain torch on every rank (bench_parity.py) ----
+    def parity_check(self, n_sample=32):
+        import bench_parity as bp
+        torch, eng, sh = self.torch, self.engine, self.shard
+        rows = torch.linspace(0, self.nq - 1, n_sample, device=self.device).long().unique()
+        rl = rows.tolist()
+        kc, k, K = self.kc, self.k, self.kc + 8
+        # the engine's per-channel lists and final result for the whole batch (all ranks take part in the collectives)
+        ed = eng.allgather_merge(*eng.dense_topk(sh.X, self.Qd, kc, sh.id_base), kc)
+        eb = eng.allgather_merge(*eng.bm25_topk(sh.bm25, self.q_indptr, self.q_term, self.mx, kc), kc)
+        es, ei = self.step()
+        # the checker's
+        rd = bp.dense_lists(sh.X, self.Qd[rows], K, sh.id_base)
+        rb = bp.bm25_lists(sh.bm25, self.q_indptr, self.q_term, rl, K)
+        out = {"queries": len(rl), "k": k, "checker": "torch fp32 matmul / fp64 scatter-add / fp32 einsum / fp64 min-max fusion per rank, "
+                                                     "merged with torch all_gather + sorts (bench_parity.py)"}
+        chans = {}
+        for name, (gs, gi), (rs, ri), tau in (("dense", ed, rd, 1e-3), ("bm25", eb, rb, 1e-3)):
+            dec, mis, rel = bp.compare(gs[rows], gi[rows], rs, ri, tau)
+            chans[name] = {"decided": dec, "mismatched_ids": mis, "max_rel_err": rel, "tau": tau}
+        # the rest of the pipeline from the checker's own channel lists
+        rdl, rbl = (rd[0][:, :kc], rd[1][:, :kc]), (rb[0][:, :kc], rb[1][:, :kc])
+        lists = [rdl, rbl]
+        weights = [0.6, 0.4]
+        if self.colbert_mode == "rerank":
+            _, cand = bp.minmax_weighted_sum([rdl, rbl], [0.6, 0.4], 2 * kc)
+            rc = bp.maxsim_candidates(sh.tokens, self.Qtok[rows], cand, sh.tok_row_base, sh.tok_rows_total, kc)
+            lists.append(rc)
+            weights.append(0.35)
+        rf = bp.minmax_weighted_sum(lists, weights, k + 8)
+        dec, mis, rel = bp.compare(es[rows], ei[rows], rf[0], rf[1], 1e-3)
+        chans["fused"] = {"decided": dec, "mismatched_ids": mis, "max_rel_err": rel, "tau": 1e-3}
+        out["channels"] = chans
+        out["mismatched_ids"] = sum(c["mismatched_ids"] for c in chans.values())
+        out["max_rel_err"] = max(c["max_rel_err"] for c in chans.values())
+        return out
 
     def cpu_sample(self, budget_s=15.0):
         """The reference's sequential path (hybrid_retriever.py:282-384) restated: flat-IP + literal BM25 + MaxSim of the
-        candidate union + _fuse, single query at a time, on a 20k-doc sample; dense and BM25 extrapolated linearly in docs."""
+        candidate union + _fuse, one query at a time per worker process, on a 20k-doc sample; dense and BM25 extrapolated
+        linearly in docs.  The reference itself is single-process; one worker per host core is the most the host can do."""
         import numpy as np
         from oracle import bm25 as obm25, dense as odense, fuse as ofuse, maxsim as omaxsim
-        n_s, v_s, nq_s = 20_000, 5_000, 4
+        n_s, v_s = 20_000, 5_000
+        workers = max(1, os.cpu_count() or 1)
+        nq_s = 2 * workers
         rng = np.random.default_rng(20)
         X = rng.standard_normal((n_s, self.d), dtype=np.float32); X /= np.linalg.norm(X, axis=1, keepdims=True)
         Q = rng.standard_normal((nq_s, self.d), dtype=np.float32); Q /= np.linalg.norm(Q, axis=1, keepdims=True)
@@ -437,27 +530,50 @@ class HybridWorkload:
         queries = [[str(t) for t in rng.choice(v_s, size=int(rng.integers(2, 9)), p=p)] for _ in range(nq_s)]
         D = rng.standard_normal((2000, self.Ld, 128), dtype=np.float32)
         Qt = rng.standard_normal((nq_s, self.Lq, 128), dtype=np.float32)
+        kc, N = self.kc, self.N
+
+        def one(j):
+            t0 = time.perf_counter()
+            ds, di = odense.flat_ip_topk(Q[j:j + 1], X, kc)
+            bs, bi = obm25.search(lit, queries[j], kc)
+            t1 = time.perf_counter()
+            dl = list(zip(di[0].tolist(), ds[0].tolist())); bl = list(zip(bi.tolist(), bs.tolist()))
+            cand = np.array([[r["id"] % 2000 for r in ofuse.fuse(dl, bl, [], method="weighted_sum")]])
+            cs = omaxsim.maxsim_scores(Qt[j:j + 1], D, None, cand)[0]
+            order = np.argsort(-cs, kind="stable")[:kc]
+            ofuse.fuse(dl, bl, [(int(cand[0][o]), float(cs[o])) for o in order], method="weighted_sum")
+            t2 = time.perf_counter()
+            return t1 - t0, t2 - t1
+        global _CPU_ONE
+        _CPU_ONE = one
 
         def run():
-            t_scan = t_rest = 0.0
-            for j in range(nq_s):
-                t0 = time.perf_counter()
-                ds, di = odense.flat_ip_topk(Q[j:j + 1], X, self.kc)
-                bs, bi = obm25.search(lit, queries[j], self.kc)
-                t1 = time.perf_counter()
-                dl = list(zip(di[0].tolist(), ds[0].tolist())); bl = list(zip(bi.tolist(), bs.tolist()))
-                cand = np.array([[r["id"] % 2000 for r in ofuse.fuse(dl, bl, [], method="weighted_sum")]])
-                cs = omaxsim.maxsim_scores(Qt[j:j + 1], D, None, cand)[0]
-                order = np.argsort(-cs, kind="stable")[:self.kc]
-                ofuse.fuse(dl, bl, [(int(cand[0][o]), float(cs[o])) for o in order], method="weighted_sum")
-                t2 = time.perf_counter()
-                t_scan += t1 - t0; t_rest += t2 - t1
-            dt = t_scan * self.N / n_s + t_rest
-            return nq_s / dt, t_scan + t_rest
-        return run, (f"oracle restatement of the reference's sequential hybrid path, one query at a time: numpy flat-IP + literal BM25Okapi over "
-                     f"{n_s} docs (extrapolated linearly to {self.N}), MaxSim of the candidate union, _fuse; {nq_s} queries per step")
+            import multiprocessing as mp
+            t0 = time.perf_counter()
+            if workers > 1:
+                with mp.get_context("fork").Pool(workers) as pool:         # forked workers share the sample corpus
+                    parts = pool.map(_cpu_one, range(nq_s))
+            else:
+                parts = [one(j) for j in range(nq_s)]
+            wall = time.perf_counter() - t0
+            # per-query cost on the full shard: the scans scale linearly in documents, the rest does not
+            t_scan, t_rest = sum(a for a, _ in parts), sum(b for _, b in parts)
+            per_query_full = (t_scan * N / n_s + t_rest) / nq_s
+            return workers / per_query_full, wall
+        return run, (f"oracle restatement of the reference's sequential hybrid path, one query at a time in each of {workers} worker processes: "
+                     f"numpy flat-IP + literal BM25Okapi over {n_s} docs (extrapolated linearly to {N}), MaxSim of the candidate union, _fuse; "
+                     f"{nq_s} queries per step")
 
-    cpu_cores = 1
+    @property
+    def cpu_cores(self):
+        return max(1, os.cpu_count() or 1)
+
+
+_CPU_ONE = None
+
+
+def _cpu_one(j):
+    return _CPU_ONE(j)
 
 
 class MaxsimScanWorkload:
@@ -632,11 +748,33 @@ WORKLOADS = {"dense": DenseWorkload, "maxsim": MaxsimWorkload, "maxsim_scan": Ma
 
 
 # =================================================================================================
+def pin_host_threads():
+    """The reference arm runs under torchrun at N > 1, which exports OMP_NUM_THREADS=1: numpy's BLAS would run on one thread
+    while the line claims all cores (round-1 finding).  Set the thread counts explicitly before numpy is imported and report
+    what the BLAS pool actually uses."""
+    n = str(max(1, os.cpu_count() or 1))
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = n
+    import numpy  # noqa: F401
+    used = int(n)
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=int(n))
+        pools = [p.get("num_threads", 0) for p in threadpool_info() if p.get("user_api") == "blas"]
+        if pools:
+            used = max(pools)
+    except Exception:
+        pass
+    return used
+
+
 def run_reference(args, rank, world):
     """The reference's CPU implementation of the path (oracle port; the third-party wheels it calls are not
     installable here) on the host cores."""
     if rank != 0:
         return
+    blas_threads = pin_host_threads()
+
     def timed(name):
         wl = WORKLOADS[name](args, 0, world, None)      # same config object as the native arm at this world size
         run, sample = wl.cpu_sample()
@@ -650,21 +788,16 @@ def run_reference(args, rank, world):
         return wl, value, 1e3 * t / args.steps, sample
 
     # A host answers N shards one after the other: N times the work in N times the time, so the metric's
-    # "rank-level query scans per second" does not depend on N for the CPU path.
+    # "shard-level query scans per second" does not depend on N for the CPU path.
     wl, value, ms, sample = timed(args.workload)
-    cores = getattr(wl, "cpu_cores", os.cpu_count())
+    cores = getattr(wl, "cpu_cores", blas_threads)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": wl.config(),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "blas_threads": blas_threads, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    if args.workload == "dense" and not args.no_hybrid_block and not (args.n_docs or args.dim or args.nq):
-        wl_h, v_h, ms_h, sample_h = timed("hybrid")      # the counterpart of the native arm's "hybrid" object
-        line["hybrid"] = {"value": v_h, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "ms_per_step": ms_h, "config": wl_h.config(),
-                          "cpu_baseline": {"value": v_h, "unit": UNIT, "cores": getattr(wl_h, "cpu_cores", os.cpu_count()), "kind": "port",
-                                           "sample": sample_h},
-                          "e2e": {"value": v_h, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -675,6 +808,10 @@ def with_burst(roof, peaks):
     if roof.get("bound") == "tensor":
         roof["peak_burst"] = peaks["bf16_tflops_burst"]
         roof["frac_of_burst"] = roof["achieved"] / peaks["bf16_tflops_burst"]
+    for st in roof.get("stages", []):
+        if st.get("bound") == "tensor":
+            st["peak_burst"] = peaks["bf16_tflops_burst"]
+            st["frac_of_burst"] = st["achieved"] / peaks["bf16_tflops_burst"]
     return roof
 
 
@@ -689,7 +826,7 @@ def release(wl):
     torch.cuda.empty_cache()
 
 
-def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks):
+def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks, e2e=True, clocks=True):
     """Sets a workload up, times `steps` steps after `warmup` (barrier + synchronize on both sides, CUDA events, max over ranks),
     then the same through the host-buffer API.  Returns the JSON line's fields on rank 0, None elsewhere."""
     import torch
@@ -705,10 +842,10 @@ def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks):
     for _ in range(warmup):
         wl.step()
     barrier()
-    engine.prof_enable(steps * 16 + 8)
+    engine.prof_enable(steps * 24 + 8)
     launches0 = engine.launch_count()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and clocks:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -717,43 +854,192 @@ def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks):
         wl.step()
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clk = sampler.stop() if rank == 0 and clocks else None
     ms = ev0.elapsed_time(ev1)
     launches = engine.launch_count() - launches0
     prof = engine.prof_collect()
     engine.prof_enable(0)
-    kern = [t for name, t in prof if name == wl.dominant]
-    kernel_ms = sum(kern) / steps        # per step (a step may launch the dominant kernel several times)
+    by_tag = {}
+    for name, t in prof:
+        by_tag[name] = by_tag.get(name, 0.0) + t / steps      # per step (a step may launch a kernel family several times)
+    tags = sorted(by_tag)
 
     # ---- end to end through the host-buffer API: H2D queries -> search -> D2H results, every step ----
-    for _ in range(2):
-        wl.e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        wl.e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = e0.elapsed_time(e1)
+    e2e_ms = 0.0
+    if e2e:
+        for _ in range(2):
+            wl.e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            wl.e2e_step()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=device)
+    t = torch.tensor([ms, e2e_ms] + [by_tag[n] for n in tags], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = t.tolist()
+    vals = t.tolist()
+    ms, e2e_ms = vals[0], vals[1]
+    by_tag = dict(zip(tags, vals[2:]))
     if rank != 0:
         return None
     units = wl.units_per_step() * steps
-    h2d, d2h = wl.e2e_bytes()
-    return {"metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+    roof = wl.roofline(by_tag, peaks) if hasattr(wl, "stage_rooflines") else wl.roofline(by_tag.get(wl.dominant, 0.0), peaks)
+    line = {"metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl.dtype,
-            "data": "synthetic (seeded, generated on device; random unit-norm vectors)", "config": wl.config(),
-            "clocks": clocks,
-            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / steps},
-            "gpu_launches": launches,
-            "roofline": with_burst(wl.roofline(kernel_ms, peaks), peaks),
-            "global_queries_per_s": wl.nq * steps / (ms * 1e-3)}
+            "data": "synthetic (seeded, generated on device; random unit-norm vectors, Zipfian postings)", "config": wl.config(),
+            "clocks": clk, "gpu_launches": launches,
+            "roofline": with_burst(roof, peaks),
+            "global_queries_per_s": wl.nq * steps / (ms * 1e-3),
+            "kernel_ms_per_step": by_tag,
+            "rest_of_step_ms": ms / steps - sum(by_tag.values())}
+    if e2e:
+        h2d, d2h = wl.e2e_bytes()
+        line["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": e2e_ms / steps}
+    return line
+
+
+# =================================================================================================
+# side blocks of the default line
+# =================================================================================================
+def kernels_block(args, device, peaks):
+    """Short runs of the other configs on one GPU, so that every kernel family has a driver-run roofline number."""
+    import copy
+    import torch
+    from legal_rag_b200 import engine
+    out = {}
+
+    def one(name, steps, **over):
+        a = copy.copy(args)
+        a.n_docs = a.dim = a.nq = a.vocab = 0
+        a.mean_len = 0.0
+        for key, v in over.items():
+            setattr(a, key, v)
+        wl = WORKLOADS[name](a, 0, 1, device)
+        try:
+            line = measure_native(wl, steps, 3, 0, 1, 0, device, peaks, e2e=False, clocks=False)
+            r = line["roofline"]
+            out[wl.name] = {"workload": line["config"]["workload"], "ms_per_step": line["ms_per_step"], "queries_per_s": line["value"],
+                            "roofline": {k: r[k] for k in ("kernel", "bound", "kernel_ms", "achieved", "peak", "unit", "frac", "algorithmic", "traffic")
+                                         if k in r}}
+            if "frac_of_burst" in r:
+                out[wl.name]["roofline"]["frac_of_burst"] = r["frac_of_burst"]
+            if "scan_gbs" in r:
+                out[wl.name]["roofline"]["scan_gbs"] = r["scan_gbs"]
+        except Exception as exc:
+            out[wl.name] = {"error": f"{type(exc).__name__}: {exc}"}
+        release(wl)
+
+    one("dense", 5)                       # configs[1]
+    cfg1 = out.pop("dense_flat_ip_top100", None)
+    one("dense", 5, nq=64)                # the same corpus, HBM-bound batch: scan GB/s
+    out["dense_flat_ip_top100_nq64"] = out.pop("dense_flat_ip_top100", None)
+    out["dense_flat_ip_top100"] = cfg1
+    one("maxsim", 5)                      # configs[2]
+    one("maxsim_scan", 3)                 # configs[2]'s store, every document
+    one("bm25", 3)                        # configs[3]
+    # top-k select over materialised score rows: the shapes the pipeline produces
+    sel = {}
+    for nq, n in ((256, 1 << 20), (64, 1 << 20), (4096, 20_000)):
+        S = torch.randn((nq, n), device=device)
+        for _ in range(3):
+            engine.topk_select(S, 100)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            engine.topk_select(S, 100)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = 4.0 * nq * n / (ms * 1e-3) / 1e9
+        sel[f"{nq}x{n}"] = {"ms": ms, "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "bound": "hbm",
+                            "algorithmic": f"4*nq*N = {4.0 * nq * n:.3e} B (select + merge launches, CUDA events around both)"}
+        del S
+    out["topk_select_k100"] = sel
+    return out
+
+
+def strong_block(args, rank, world, local_rank, device, peaks, weak_ms):
+    """Strong scaling of the hybrid step: the per-GPU shard of the weak run (what ONE GPU holds) split over the N ranks."""
+    import copy
+    a = copy.copy(args)
+    per = (12_500_000 if not args.n_docs else args.n_docs) // world
+    wl = HybridWorkload(a, rank, world, device, n_docs=per)
+    line = measure_native(wl, max(2, min(args.steps, 5)), 3, rank, world, local_rank, device, peaks, e2e=False, clocks=False)
+    release(wl)
+    if rank != 0:
+        return None
+    ms = line["ms_per_step"]
+    rest = line["rest_of_step_ms"]
+    return {"corpus_docs_total": per * world, "docs_per_gpu": per, "ms_per_step": ms, "queries_per_s": line["global_queries_per_s"],
+            "one_gpu_ms_per_step": weak_ms, "speedup_vs_one_gpu": weak_ms / ms, "efficiency": weak_ms / ms / world,
+            "kernel_ms_per_step": line["kernel_ms_per_step"], "collectives_and_glue_ms": rest,
+            "limiter": ("kernel time falls with 1/N; what does not shrink is the exchange: one packed all-gather + one max-reduce per step, "
+                        "the merge / fusion / select launches over nq x k lists and their launch gaps (collectives_and_glue_ms)"),
+            "note": "one_gpu_ms_per_step is this run's weak-scaling step (every rank scans a full single-GPU shard)"}
+
+
+def api_block(args, device):
+    """The reference's class API on configs[0]'s corpus (UCC articles; hashing stand-ins for the BGE / jieba encoders, whose
+    forward passes are not part of the path): HybridRetriever.search(question, None, 100) one query at a time and
+    HybridRetriever.search_batch, through artifacts written by this package's builders."""
+    import tempfile
+    import numpy as np
+    from legal_rag_b200.config import AppConfig
+    from legal_rag_b200.retrieval import HybridRetriever, builders, encoders
+    from legal_rag_b200.schemas import LawChunk
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ucc_corpus.npz"))
+    lens, flat, vocab, ids = z["doc_len"], z["tokens"].astype(np.int64), z["vocab"], z["ids"]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    texts = [" ".join(vocab[flat[off[i]:off[i + 1]]]) for i in range(len(lens))]
+    chunks = [LawChunk(id=str(ids[i]), law_name="UCC", article_no=str(i), article_id=str(i), text=texts[i], lang="en")
+              for i in range(len(texts))]
+    rng = np.random.default_rng(44)
+    questions = []
+    for _ in range(256):
+        t = texts[int(rng.integers(0, len(texts)))].split()
+        L = int(rng.integers(3, 9))
+        st = int(rng.integers(0, max(1, len(t) - L)))
+        questions.append(" ".join(t[st:st + L]))
+    out = {"corpus": f"configs[0]: {len(chunks)} UCC articles", "encoders": "HashingDenseEncoder(768) / regex tokenizer (stand-ins)"}
+    with tempfile.TemporaryDirectory() as root:
+        cfg = AppConfig()
+        cfg.device = str(device)
+        r = cfg.retrieval
+        r.faiss_index_file, r.faiss_meta_file = os.path.join(root, "faiss", "faiss.index"), os.path.join(root, "faiss", "faiss_meta.jsonl")
+        r.bm25_index_file = os.path.join(root, "bm25.pkl")
+        r.enable_colbert = False
+        r.top_k, r.min_final_score, r.fusion_method = 100, 0.0, "weighted_sum"
+        enc = encoders.HashingDenseEncoder(768)
+        encoders.register_dense_encoder(lambda name, dev: enc)
+        try:
+            builders.build_faiss_index(cfg, chunks)
+            builders.build_bm25_index(cfg, chunks)
+            hr = HybridRetriever(cfg)
+            for q in questions[:8]:
+                hr.search(q, None, 100)
+            t0 = time.perf_counter()
+            for q in questions[:64]:
+                hits = hr.search(q, None, 100)
+            dt = time.perf_counter() - t0
+            out["search_us_per_query"] = 1e6 * dt / 64
+            out["search_hits"] = len(hits)
+            hr.search_batch(questions, 100)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                res = hr.search_batch(questions, 100)
+            dt = time.perf_counter() - t0
+            out["search_batch_queries_per_s"] = 3 * len(questions) / dt
+            out["search_batch_size"] = len(questions)
+            out["fast_path"] = bool(getattr(hr, "fast_path_used", False))
+        finally:
+            encoders.register_dense_encoder(None)
+    return out
 
 
 def main():
@@ -762,7 +1048,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="dense", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="hybrid", choices=sorted(WORKLOADS))
     ap.add_argument("--n-docs", type=int, default=0)
     ap.add_argument("--dim", type=int, default=0)
     ap.add_argument("--vocab", type=int, default=0)
@@ -773,8 +1059,8 @@ def main():
     ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
                     help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-hybrid-block", action="store_true",
-                    help="default workload only: skip the extra 'hybrid' object (every rank's shard of configs[4] through the hybrid pipeline)")
+    ap.add_argument("--no-side-blocks", action="store_true",
+                    help="default workload only: skip parity_check / strong / kernels / api (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -794,35 +1080,44 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
-    from legal_rag_b200 import engine
 
     peaks = measured_peaks()
     wl = WORKLOADS[args.workload](args, rank, world, device)
     line = measure_native(wl, args.steps, args.warmup, rank, world, local_rank, device, peaks)
+    default_shape = args.workload == "hybrid" and not (args.n_docs or args.dim or args.nq or args.vocab) and not args.no_side_blocks
 
-    # The metric's own multi-GPU configuration next to the configs[1] line: every rank's 1/8 shard of configs[4] through the
-    # sharded hybrid pipeline (a shorter timed region; same rules).  8 ranks hold exactly configs[4].
-    if args.workload == "dense" and not args.no_hybrid_block and not (args.n_docs or args.dim or args.nq):
-        wl_h = WORKLOADS["hybrid"](args, rank, world, device)
-        release(wl)
+    def guarded(name, fn):
         try:
-            h = measure_native(wl_h, max(1, min(args.steps, 5)), args.warmup, rank, world, local_rank, device, peaks)
-        except Exception as exc:       # the configs[1] line above stands on its own
-            h = {"error": f"{type(exc).__name__}: {exc}"}
-        release(wl_h)
+            return fn()
+        except Exception as exc:       # the main line stands on its own
+            import traceback
+            traceback.print_exc()
+            return {"error": f"{type(exc).__name__}: {exc}"}
+
+    if hasattr(wl, "parity_check") and not args.no_side_blocks:
+        pc = guarded("parity_check", wl.parity_check)           # every rank takes part in its collectives
         if rank == 0:
-            line["hybrid"] = h if "error" in h else {key: h[key] for key in ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "config",
-                                                      "clocks", "e2e", "gpu_launches", "roofline", "global_queries_per_s")}
+            line["parity_check"] = pc
+    release(wl)
+    if default_shape and world > 1:
+        sb = guarded("strong", lambda: strong_block(args, rank, world, local_rank, device, peaks, line["ms_per_step"] if rank == 0 else 0.0))
+        if rank == 0:
+            line["strong"] = sb
+    if default_shape and world == 1:
+        line["kernels"] = guarded("kernels", lambda: kernels_block(args, device, peaks))
+        line["api"] = guarded("api", lambda: api_block(args, device))
 
     if rank == 0:
         if not args.no_cpu_baseline:
+            blas_threads = pin_host_threads()
             run, sample = wl.cpu_sample()
             run()
             vals, t0 = [], time.perf_counter()
             while time.perf_counter() - t0 < 12.0 and len(vals) < 20:
                 vals.append(run()[0])
             v = len(vals) / sum(1.0 / x for x in vals)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": getattr(wl, "cpu_cores", os.cpu_count()), "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": getattr(wl, "cpu_cores", blas_threads), "kind": "port", "sample": sample,
+                                    "blas_threads": blas_threads}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

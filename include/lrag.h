@@ -14,8 +14,13 @@
  *     <fn>_workspace_bytes(...) bytes, 256-byte aligned;
  *   - return 0 on success, a negative LRAG_E* code otherwise; lrag_last_error() gives
  *     the thread-local message;
- *   - no global mutable state after lrag_init: callable concurrently from any host
- *     thread on distinct streams with distinct workspaces;
+ *   - one process per GPU.  After lrag_init the scoring entry points keep no state of their
+ *     own between calls and may be called concurrently from any host thread on distinct
+ *     streams with distinct workspaces.  Process-wide state exists in three places and is
+ *     documented where it is declared: the device binding of lrag_init, the launch profiler
+ *     (lrag_prof_*, benchmarks only, not thread-safe) and the BM25 item-size knob
+ *     (lrag_bm25_set_item_slabs, set once before serving).  Kernel attributes are cached per
+ *     device, so a second device bound in the same process launches correctly;
  *   - no CPU fallback: lrag_init fails on anything that is not compute capability 10.x.
  *
  * Result ordering everywhere: (score descending, id ascending); rows shorter than k are
@@ -89,7 +94,10 @@ int lrag_dense_topk_bf16_ref(const void* X, int64_t N, int d, const void* Q, int
  * of each row are live).  Replaces the `sorted(range(N), key=scores[i], reverse=True)[:k]`
  * of legalrag/retrieval/bm25_retriever.py:75 for small corpora and ranks MaxSim
  * candidate scores.  If `col_id` is non-NULL ([nq, N] int64) the returned id is
- * col_id[row, col] (entries with col_id < 0 are skipped); else id_base + col.
+ * col_id[row, col] (entries with col_id < 0 are skipped; ids of any 64-bit width: they never
+ * pass through the 32-bit tie field of the selection keys, equal scores are ordered by id
+ * when the hits are written, and which of several EQUAL scores make the cut at rank k is
+ * decided by column); else id_base + col.
  * With a workspace of lrag_topk_select_workspace_bytes() long rows are streamed once by a
  * one-wave grid (per-CTA candidate lists in the workspace, then a merge); without one
  * (ws NULL) every row is selected by a single CTA. */
@@ -100,9 +108,19 @@ int lrag_topk_select_f32(const float* S, int64_t ld, int nq, int64_t N, int k, i
 
 /* k-way merge of per-shard candidate lists (the step after the NCCL all-gather; no
  * reference counterpart -- the reference is single-process).  score/id [nq, L];
- * id < 0 entries are padding. */
+ * id < 0 entries are padding.  Ids are full 64-bit values: a row whose ids span less than
+ * 2^32 - 1 (any sharded corpus below 4 G documents) is ordered exactly (score desc, id asc);
+ * a wider row is ordered the same way, except that which of several EQUAL scores make the
+ * cut at rank k is decided by position in the input row.
+ * lrag_topk_merge_shards reads the all-gathered buffers in place: `shards` blocks of
+ * [nq, kin], shard g's block starting score_shard_stride / id_shard_stride ELEMENTS after
+ * shard g - 1's (a packed all-gather of several channels passes each channel's offset into
+ * the rank-0 block and the per-rank buffer length). */
 int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k,
                     float* out_score, int64_t* out_id, lrag_stream_t stream);
+int lrag_topk_merge_shards(const float* score, const int64_t* id, int64_t score_shard_stride,
+                           int64_t id_shard_stride, int shards, int nq, int kin, int k,
+                           float* out_score, int64_t* out_id, lrag_stream_t stream);
 
 /* Gathered inner products: out_score[q, c] = <Q[q], X[rows[q, c]]> (rows outside [0, N) give -inf).
  * Replaces the re-embedding + cosine loop of the graph-expansion channel

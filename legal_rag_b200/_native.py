@@ -39,6 +39,7 @@ SIGNATURES = {
     "lrag_topk_select_workspace_bytes": (_c_sz, [_c_int, _c_i64, _c_int]),
     "lrag_topk_select_f32": (_c_int, [_c_p, _c_i64, _c_int, _c_i64, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_topk_merge": (_c_int, [_c_p, _c_p, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p]),
+    "lrag_topk_merge_shards": (_c_int, [_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p]),
     "lrag_bm25_topk_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_i64]),
     "lrag_bm25_set_item_slabs": (_c_int, [_c_int]),
     "lrag_bm25_topk": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_int, _c_i64, _c_int,

@@ -32,31 +32,37 @@ topk_select_kernel(const float* S, int64_t ld, int64_t N, int k, int64_t id_base
                     out_score + size_t(q) * k, out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), rows.col_id);
 }
 
-// (score, id) pairs of one row.  Narrow rows (max id - min id < 2^32 - 1: every sharded corpus below 4 G docs) keep the
-// exact (score desc, id asc) order through the key's tie field = id - min id; wider rows key on the entry index and
-// look the 64-bit id up when the hit is written.
+// (score, id) pairs of one row, spread over `shards` lists of `kin` entries: entry c = (shard c / kin, rank c % kin) lives at
+// score[shard * shard_stride + c % kin] (one list: shards = 1).  Narrow rows (max id - min id < 2^32 - 1: every sharded corpus
+// below 4 G docs) keep the exact (score desc, id asc) order through the key's tie field = id - min id; wider rows key on the
+// entry index and look the 64-bit id up when the hit is written.
 struct RowPairs {
-  const float* s; const int64_t* id; int n; int64_t base; bool wide;
+  const float* s; const int64_t* id; int kin, n; int64_t s_stride, i_stride; int64_t base; bool wide;
+  __device__ __forceinline__ float score_at(int c) const { return s[int64_t(c / kin) * s_stride + c % kin]; }
+  __device__ __forceinline__ int64_t id_at(int c) const { return id[int64_t(c / kin) * i_stride + c % kin]; }
   template <class F> __device__ void operator()(F&& f) const {
     for (int c = threadIdx.x; c < n; c += SELECT_THREADS) {
-      const int64_t i = id[c];
-      if (i >= 0) f(make_key(s[c], wide ? uint32_t(c) : uint32_t(i - base)));
+      const int64_t i = id_at(c);
+      if (i >= 0) f(make_key(score_at(c), wide ? uint32_t(c) : uint32_t(i - base)));
     }
   }
 };
 
+// score / id point at shard 0's list of row 0; a row's lists are `kin` apart inside a shard, shards are *_stride apart
 __global__ void __launch_bounds__(SELECT_THREADS)
-topk_merge_kernel(const float* score, const int64_t* id, int L, int k, int P, float* out_score, int64_t* out_id) {
+topk_merge_kernel(const float* score, const int64_t* id, int64_t s_stride, int64_t i_stride, int shards, int kin, int k, int P,
+                  int ids_fit, float* out_score, int64_t* out_id) {
   extern __shared__ uint8_t sm_raw[];
   __shared__ SelectShared ss;
   __shared__ long long id_min, id_max;
   const int q = blockIdx.x;
-  const int64_t* ids = id + size_t(q) * L;
+  const int L = shards * kin;
+  RowPairs rows{score + size_t(q) * kin, id + size_t(q) * kin, kin, L, s_stride, i_stride, 0, false};
   if (threadIdx.x == 0) { id_min = LLONG_MAX; id_max = -1; }
   __syncthreads();
   long long lo = LLONG_MAX, hi = -1;
   for (int c = threadIdx.x; c < L; c += SELECT_THREADS) {
-    const long long i = ids[c];
+    const long long i = rows.id_at(c);
     if (i >= 0) { lo = i < lo ? i : lo; hi = i > hi ? i : hi; }
   }
 #pragma unroll
@@ -66,10 +72,21 @@ topk_merge_kernel(const float* score, const int64_t* id, int L, int k, int P, fl
   }
   if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(&id_min, lo); atomicMax(&id_max, hi); }
   __syncthreads();
-  const bool wide = id_max >= 0 && (unsigned long long)(id_max - id_min) >= 0xffffffffull;
-  RowPairs rows{score + size_t(q) * L, ids, L, id_max >= 0 ? id_min : 0, wide};
-  block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), rows.base, out_score + size_t(q) * k,
-                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), wide ? ids : nullptr);
+  rows.wide = id_max >= 0 && (unsigned long long)(id_max - id_min) >= 0xffffffffull;
+  rows.base = id_max >= 0 ? id_min : 0;
+  // wide rows: the tie field is the entry index; the lookup table of the output stage is the id list itself, which is
+  // contiguous only for a single list -- several lists go through a gather of the ids into shared memory first
+  const int64_t* lookup = nullptr;
+  int64_t* ids_sm = reinterpret_cast<int64_t*>(sm_raw + size_t(P) * 8);
+  if (rows.wide && ids_fit) {
+    for (int c = threadIdx.x; c < L; c += SELECT_THREADS) ids_sm[c] = rows.id_at(c);
+    __syncthreads();
+    lookup = ids_sm;
+  } else if (rows.wide) {
+    lookup = rows.id;          // a single list too long for shared memory is contiguous in global memory
+  }
+  block_topk_sorted(rows, k, P, ss, reinterpret_cast<uint64_t*>(sm_raw), rows.wide ? 0 : rows.base, out_score + size_t(q) * k,
+                    out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), lookup);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -498,15 +515,43 @@ extern "C" int lrag_topk_select_f32(const float* S, int64_t ld, int nq, int64_t 
                             static_cast<cudaStream_t>(stream), ws, ws_bytes);
 }
 
+static int launch_topk_merge(const float* score, const int64_t* id, int64_t s_stride, int64_t i_stride, int shards, int nq, int kin,
+                             int k, float* out_score, int64_t* out_id, cudaStream_t stream) {
+  const int P = next_pow2(k);
+  // sorted keys [P] + (wide ids only) the row's ids [shards * kin]
+  size_t smem = select_smem_bytes(k) + size_t(shards) * kin * 8;
+  const bool ids_fit = smem <= 200 * 1024;
+  LRAG_REQUIRE(ids_fit || shards == 1, "topk_merge: %d lists of %d entries do not fit one CTA's shared memory", shards, kin);
+  if (!ids_fit) smem = select_smem_bytes(k);
+  static size_t smem_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
+  const int dev = device_slot();
+  if (smem > 48 * 1024 && smem > smem_set[dev]) {
+    LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    smem_set[dev] = smem;
+  }
+  topk_merge_kernel<<<nq, SELECT_THREADS, smem, stream>>>(score, id, s_stride, i_stride, shards, kin, k, P, ids_fit ? 1 : 0, out_score, out_id);
+  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+  return LRAG_OK;
+}
+
 extern "C" int lrag_topk_merge(const float* score, const int64_t* id, int nq, int L, int k, float* out_score,
                                int64_t* out_id, lrag_stream_t stream) {
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && L >= 0 && k > 0 && k <= LRAG_MAX_K, "topk_merge: bad shape nq=%d L=%d k=%d", nq, L, k);
   LRAG_REQUIRE((score && id) || L == 0, "topk_merge: null pointer");
   LRAG_REQUIRE(out_score && out_id, "topk_merge: null output");
-  const int P = next_pow2(k);
-  topk_merge_kernel<<<nq, SELECT_THREADS, select_smem_bytes(k), static_cast<cudaStream_t>(stream)>>>(
-      score, id, L, k, P, out_score, out_id);
-  LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
-  return LRAG_OK;
+  return launch_topk_merge(score, id, 0, 0, 1, nq, L, k, out_score, out_id, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lrag_topk_merge_shards(const float* score, const int64_t* id, int64_t score_shard_stride, int64_t id_shard_stride,
+                                      int shards, int nq, int kin, int k, float* out_score, int64_t* out_id, lrag_stream_t stream) {
+  LRAG_REQUIRE(initialised(), "lrag_init has not been called");
+  LRAG_REQUIRE(nq > 0 && shards > 0 && kin > 0 && k > 0 && k <= LRAG_MAX_K, "topk_merge_shards: bad shape shards=%d nq=%d kin=%d k=%d",
+               shards, nq, kin, k);
+  LRAG_REQUIRE(score && id && out_score && out_id, "topk_merge_shards: null pointer");
+  LRAG_REQUIRE(score_shard_stride >= int64_t(nq) * kin && id_shard_stride >= int64_t(nq) * kin,
+               "topk_merge_shards: shard strides (%lld, %lld elements) are shorter than one shard's [nq, kin] block",
+               (long long)score_shard_stride, (long long)id_shard_stride);
+  return launch_topk_merge(score, id, score_shard_stride, id_shard_stride, shards, nq, kin, k, out_score, out_id,
+                           static_cast<cudaStream_t>(stream));
 }

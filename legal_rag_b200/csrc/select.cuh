@@ -109,7 +109,7 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* key, int P, Bar bar = 
 // (LRAG_PAD_SCORE, -1).  out_key, if non-null, receives the k winning keys (0 = empty).
 // `lookup` == null: a key's tie field is a local id and the hit's id is id_base + that.
 // `lookup` != null: the tie field is an index into `lookup` (ids of any width; 64-bit ids never pass through
-// the 32-bit field): the hit's id is lookup[index], and hits of equal score are put in ascending id order
+// the 32-bit field): the hit's id is id_base + lookup[index], and hits of equal score are put in ascending id order
 // afterwards (which of several equal scores make the cut at rank k is then decided by index, not by id).
 template <class ForEach>
 __device__ int block_topk_sorted(const ForEach& for_each, int k, int P, SelectShared& sm, uint64_t* sel_key,
@@ -147,7 +147,7 @@ __device__ int block_topk_sorted(const ForEach& for_each, int k, int P, SelectSh
       pos += (idj < id || (idj == id && j < r)) ? 1 : 0;
     }
     out_score[pos] = key_score(key);
-    out_id[pos] = id;
+    out_id[pos] = id_base + id;
   }
   __syncthreads();
   return n;

@@ -110,6 +110,20 @@ def topk_select(S: torch.Tensor, k: int, id_base: int = 0, col_id: Optional[torc
     return s, i
 
 
+def topk_merge_shards(gs: torch.Tensor, gi: torch.Tensor, k: int, s_stride: Optional[int] = None, i_stride: Optional[int] = None,
+                      shards: Optional[int] = None, nq: Optional[int] = None, kin: Optional[int] = None):
+    """k-way merge straight from all-gathered buffers: gs / gi are [shards, nq, kin] (or views into a packed gather whose
+    per-shard strides, in elements, are given explicitly): no permute / copy between the collective and the merge."""
+    lib = _native.init(gs.device.index)
+    if shards is None:
+        shards, nq, kin = gs.shape
+        s_stride, i_stride = gs.stride(0), gi.stride(0)
+    s, i = _out(nq, k, gs.device)
+    check(lib.lrag_topk_merge_shards(_ptr(gs), _ptr(gi), int(s_stride), int(i_stride), int(shards), int(nq), int(kin), int(k),
+                                     _ptr(s), _ptr(i), _stream()), "lrag_topk_merge_shards")
+    return s, i
+
+
 def topk_merge(scores: torch.Tensor, ids: torch.Tensor, k: int):
     """k-way merge of concatenated per-shard lists [nq, L] (id < 0 = padding)."""
     lib = _native.init(scores.device.index)
@@ -347,9 +361,11 @@ def allgather_merge(scores: torch.Tensor, ids: torch.Tensor, k: int, group=None,
     dist.all_gather_into_tensor(gs, scores.contiguous(), group=group)
     dist.all_gather_into_tensor(gi, ids.contiguous(), group=group)
     gs, gi = gs.view(world, nq, k), gi.view(world, nq, k)
+    if merge is None:
+        return topk_merge_shards(gs, gi, k)           # the merge kernel reads the gathered layout in place
     cat_s = gs.permute(1, 0, 2).reshape(nq, world * k).contiguous()
     cat_i = gi.permute(1, 0, 2).reshape(nq, world * k).contiguous()
-    return (merge or topk_merge)(cat_s, cat_i, k)
+    return merge(cat_s, cat_i, k)
 
 
 def allgather_merge_many(lists, k: int, group=None, merge=None):
@@ -360,20 +376,32 @@ def allgather_merge_many(lists, k: int, group=None, merge=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return list(lists)
     world = dist.get_world_size(group)
-    flat = [t.contiguous().view(torch.uint8).reshape(-1) for pair in lists for t in pair]
-    sizes = [f.numel() for f in flat]
+    # every part padded to 16 bytes so that each channel's scores / ids stay aligned inside the packed buffer
+    flat, offs, off = [], [], 0
+    for pair in lists:
+        for t in pair:
+            b = t.contiguous().view(torch.uint8).reshape(-1)
+            pad = (-b.numel()) % 16
+            flat.append(b if pad == 0 else torch.nn.functional.pad(b, (0, pad)))
+            offs.append(off)
+            off += b.numel() + pad
     mine = torch.cat(flat)
     gathered = torch.empty((world, mine.numel()), dtype=torch.uint8, device=mine.device)
     dist.all_gather_into_tensor(gathered.view(-1), mine, group=group)
-    out, off = [], 0
+    out = []
     for n, (sc, ids) in enumerate(lists):
         nq = sc.shape[0]
+        if merge is None and sc.dtype == torch.float32 and ids.dtype == torch.int64:
+            # the merge kernel reads each channel's lists out of the packed gather in place
+            gs = gathered[0, offs[2 * n]:].view(torch.float32)
+            gi = gathered[0, offs[2 * n + 1]:].view(torch.int64)
+            out.append(topk_merge_shards(gs, gi, k, s_stride=mine.numel() // 4, i_stride=mine.numel() // 8, shards=world, nq=nq, kin=k))
+            continue
         parts = []
-        for t in (sc, ids):
-            nb = sizes[len(parts) + 2 * n]
-            g = gathered[:, off:off + nb].contiguous().view(t.dtype).view(world, nq, k)
+        for j, t in enumerate((sc, ids)):
+            nb = t.numel() * t.element_size()
+            g = gathered[:, offs[2 * n + j]:offs[2 * n + j] + nb].contiguous().view(t.dtype).view(world, nq, k)
             parts.append(g.permute(1, 0, 2).reshape(nq, world * k).contiguous())
-            off += nb
         out.append((merge or topk_merge)(parts[0], parts[1], k))
     return out
 
@@ -455,10 +483,15 @@ class GraphedHybridQuery:
     """
 
     def __init__(self, X: torch.Tensor, bm25: Bm25DeviceIndex, k: int = 100, nq: int = 1, max_terms: int = 32, id_base: int = 0,
-                 method: str = "weighted_sum", w_dense: float = 0.6, w_bm25: float = 0.4, **fuse_kw):
+                 method: str = "weighted_sum", w_dense: float = 0.6, w_bm25: float = 0.4, kc: Optional[int] = None,
+                 breakdown: bool = False, **fuse_kw):
+        """k: hits returned; kc: per-channel list length (default k); breakdown: also return the fusion breakdown [nq, k, 8]
+        and the two channels' id lists (what HybridRetriever.search needs to rebuild the reference's score_breakdown)."""
         self.X = _need(X, torch.bfloat16, 2, "X")
         self.bm25, self.nq, self.max_terms = bm25, int(nq), int(max_terms)
-        self.k = min(int(k), int(X.shape[0]))
+        self.kc = min(int(kc if kc is not None else k), int(X.shape[0]), LRAG_MAX_K)
+        self.k = min(int(k), 2 * self.kc)
+        self.breakdown = bool(breakdown)
         dev = X.device
         self.Q = torch.zeros((nq, X.shape[1]), dtype=torch.bfloat16, device=dev)
         self.q_indptr = torch.zeros(nq + 1, dtype=torch.int64, device=dev)
@@ -468,6 +501,10 @@ class GraphedHybridQuery:
         self._h_term = torch.full((nq * max_terms,), -1, dtype=torch.int32).pin_memory()
         self._h_s = torch.empty((nq, self.k), dtype=torch.float32).pin_memory()
         self._h_i = torch.empty((nq, self.k), dtype=torch.int64).pin_memory()
+        if self.breakdown:
+            self._h_bd = torch.empty((nq, self.k, len(BREAKDOWN_FIELDS)), dtype=torch.float32).pin_memory()
+            self._h_di = torch.empty((nq, self.kc), dtype=torch.int64).pin_memory()
+            self._h_bi = torch.empty((nq, self.kc), dtype=torch.int64).pin_memory()
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, **fuse_kw)
 
         branch = torch.cuda.Stream(device=dev)
@@ -478,10 +515,10 @@ class GraphedHybridQuery:
             main = torch.cuda.current_stream(dev)
             branch.wait_stream(main)
             with torch.cuda.stream(branch):
-                b = bm25_topk(self.bm25, self.q_indptr, self.q_term, self.max_terms, self.k)
-            d = dense_topk(self.X, self.Q, self.k, id_base)
+                b = bm25_topk(self.bm25, self.q_indptr, self.q_term, self.max_terms, self.kc)
+            d = dense_topk(self.X, self.Q, self.kc, id_base)
             main.wait_stream(branch)
-            return fuse_topk(d, b, None, k=self.k, **kw)
+            return fuse_topk(d, b, None, k=self.k, breakdown=self.breakdown, **kw), d[1], b[1]
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -492,7 +529,9 @@ class GraphedHybridQuery:
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out_s, self.out_i = run()
+            fused, self.out_di, self.out_bi = run()
+            self.out_s, self.out_i = fused[0], fused[1]
+            self.out_bd = fused[2] if self.breakdown else None
 
     def search(self, Q_host: torch.Tensor, terms):
         """Q_host [nq, d] (CPU, fp32 or bf16); terms: nq lists of int term ids (-1 = out of vocabulary, repeats kept)."""
@@ -515,6 +554,10 @@ class GraphedHybridQuery:
         self.graph.replay()
         self._h_s.copy_(self.out_s, non_blocking=True)
         self._h_i.copy_(self.out_i, non_blocking=True)
+        if self.breakdown:
+            self._h_bd.copy_(self.out_bd, non_blocking=True)
+            self._h_di.copy_(self.out_di, non_blocking=True)
+            self._h_bi.copy_(self.out_bi, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self._h_s, self._h_i
 

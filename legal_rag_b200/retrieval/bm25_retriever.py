@@ -3,6 +3,7 @@ when rank_bm25 is not installed), converted once to device-resident CSR postings
 liblrag BM25 kernel -- scoring and the full ranking the reference does in Python."""
 from __future__ import annotations
 
+import logging
 from pathlib import Path
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -53,7 +54,14 @@ class BM25Retriever:
         self.load()
         host, dev = self.host_index, self.device_index
         k = max(1, min(int(top_k), engine.LRAG_MAX_K))
-        token_lists = [list(t)[: engine.LRAG_BM25_MAX_QUERY_TERMS] for t in token_lists]
+        token_lists = [list(t) for t in token_lists]
+        longest = max((len(t) for t in token_lists), default=0)
+        if longest > engine.LRAG_BM25_MAX_QUERY_TERMS:
+            # rank_bm25 scores every token (bm25_retriever.py:74); the kernel's per-query term table holds 128
+            logging.getLogger("legal_rag_b200.retrieval").warning(
+                "[BM25] a query of %d tokens is scored on its first %d (kernel limit LRAG_BM25_MAX_QUERY_TERMS); the reference "
+                "would score all of them", longest, engine.LRAG_BM25_MAX_QUERY_TERMS)
+            token_lists = [t[: engine.LRAG_BM25_MAX_QUERY_TERMS] for t in token_lists]
         qi, qt, mx = host.encode_queries(token_lists)
         return engine.bm25_topk(dev, torch.from_numpy(qi).to(self.device), torch.from_numpy(qt).to(self.device), mx, k)
 

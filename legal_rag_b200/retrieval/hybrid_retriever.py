@@ -103,6 +103,10 @@ class HybridRetriever:
             except Exception as exc:
                 print("[HybridRetriever] ColBERT init failed:", repr(exc))
                 traceback.print_exc()
+        self._align_key = None   # (store / index mtimes) the alignment verdict below was computed for
+        self._aligned = False
+        self._graphs: Dict[Any, Any] = {}     # captured single-query pipelines, by (depth, top_k, fusion knobs, store snapshot)
+        self.fast_path_used = False
         self.graph = None        # plug a retrieval.GraphRetriever(cfg, graph=<graph store with walk()>) in here: the graph
                                  # store is host-side and injected, its scoring stage runs on the GPU
         self.reranker = None     # optional callable(question, hits) -> hits (cross-encoder rerank is out of scope)
@@ -164,7 +168,12 @@ class HybridRetriever:
         rcfg = self.cfg.retrieval
         top_k = max(1, int(top_k))
         depth = max(top_k, int(getattr(rcfg, "top_k", top_k * 8) or (top_k * 8)))     # per-channel oversampling
+        depth = min(depth, engine.LRAG_MAX_K)                                         # the kernels' list length limit
+        top_k = min(top_k, 3 * depth)
         laps = _Laps()
+        fast = self._search_graphed(question, top_k, depth, decision, laps)
+        if fast is not None:
+            return fast
         per_channel = {}
         for name, channel in (("dense", self.search_dense), ("bm25", self.search_bm25), ("colbert", self.search_colbert)):
             per_channel[name] = channel(question, depth)
@@ -260,22 +269,92 @@ class HybridRetriever:
             out.append(RetrievalHit(chunk=chunk_of[j], score=float(score), rank=r, source="retriever", score_breakdown=sb))
         return out
 
+    # ------------------------------------------------------------------ shared-row check, single-query fast path
+    def _stores_aligned(self) -> bool:
+        """True when the dense store, the BM25 index (and the ColBERT meta) list the same chunks in the same order -- what
+        scripts.build_index produces -- so that a row number means the same chunk in every channel.  The O(N) comparison
+        runs once per store snapshot (keyed by the files' mtimes), not per call."""
+        self.dense.store.load()
+        self.bm25.load()
+        key = (self.dense.store._index_mtime, self.dense.store._meta_mtime, self.bm25._bm25_mtime,
+               None if self.colbert is None else self.colbert._meta_mtime)
+        if key != self._align_key:
+            chunks = self.dense.store.chunks
+            ok = len(chunks) == len(self.bm25.chunks) and all(a.id == b.id for a, b in zip(chunks, self.bm25.chunks))
+            if ok and self.colbert is not None:
+                p2c = self.colbert._pid2chunk
+                ok = len(p2c) == len(chunks) and all(p2c.get(i) is not None and p2c[i].id == c.id for i, c in enumerate(chunks))
+            self._aligned, self._align_key = ok, key
+            self._graphs.clear()                  # captured pipelines hold the old snapshot's device tensors
+        return self._aligned
+
+    def _search_graphed(self, question: str, top_k: int, depth: int, decision: Any, laps: "_Laps") -> Optional[List[RetrievalHit]]:
+        """search() for the common online case -- dense + BM25 channels over row-aligned stores, no ColBERT channel, no graph
+        expansion asked for, no reranker -- as ONE captured CUDA graph per query (engine.GraphedHybridQuery: both scans on
+        forked streams, fusion with min_final_score and the breakdown, ~100 us on configs[0]'s corpus) instead of three
+        synchronising channel calls and a host-side fusion set-up.  Returns None when the case does not apply; results are
+        those of the general path (same kernels; `tests/test_gpu_retrievers.py::test_search_fast_path_equals_general_path`)."""
+        rcfg = self.cfg.retrieval
+        mode = getattr(decision, "mode", None)
+        if (self.colbert is not None or (getattr(rcfg, "enable_rerank", False) and self.reranker is not None)
+                or (getattr(rcfg, "enable_graph", False) and self.graph is not None and mode and str(mode).upper().endswith("GRAPH_AUGMENTED"))):
+            return None
+        if not self._stores_aligned():
+            return None
+        store, bm = self.dense.store, self.bm25
+        tokens = bm.tokenizer(question)
+        max_terms = 64
+        if len(tokens) > max_terms or store.index.ntotal != len(store.chunks) or store.index.ntotal == 0:
+            return None
+        knobs = self._fusion_knobs()
+        floor = float(getattr(rcfg, "min_final_score", 0.0))
+        key = (depth, top_k, tuple(sorted(knobs.items())), floor, id(store.index), id(bm.device_index))
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 32:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = engine.GraphedHybridQuery(
+                store.index.matrix, bm.device_index, k=top_k, kc=depth, nq=1, max_terms=max_terms, breakdown=True,
+                method=knobs["method"], w_dense=knobs["w_dense"], w_bm25=knobs["w_bm25"], w_colbert=knobs["w_colbert"],
+                rrf_k=knobs["rrf_k"], alpha=knobs["alpha"], min_final=floor)
+        q_vec = torch.from_numpy(store._embed([question], is_query=True))
+        _, qt, _ = bm.host_index.encode_queries([tokens])
+        fs, fi = g.search(q_vec, [qt.tolist()])
+        laps.mark("dense"); laps.mark("bm25"); laps.mark("colbert"); laps.mark("fuse")
+        in_dense, in_bm25 = set(g._h_di[0].tolist()), set(g._h_bi[0].tolist())
+        weights = {"dense": knobs["w_dense"], "bm25": knobs["w_bm25"], "colbert": knobs["w_colbert"]}
+        chunks = store.chunks
+        out: List[RetrievalHit] = []
+        for r, (score, j, b) in enumerate(zip(fs[0].tolist(), fi[0].tolist(), g._h_bd[0].tolist()), start=1):
+            if j < 0:
+                break
+            contrib = {"dense": b[5], "bm25": b[6], "colbert": b[7]}
+            member = [c for c, inside in (("dense", j in in_dense), ("bm25", j in in_bm25)) if inside]
+            member.sort(key=lambda c: (float(contrib.get(c, 0.0)), str(c)), reverse=True)
+            sb = {"fusion_method": knobs["method"], "rrf_k": knobs["rrf_k"], "alpha": knobs["alpha"], "channel_weights": dict(weights),
+                  "channel": member, "channel_contrib": contrib, "rrf_norm": b[0], "weighted_sum": b[1], "dense_norm": b[2],
+                  "bm25_norm": b[3], "colbert_norm": b[4]}
+            out.append(RetrievalHit(chunk=chunks[j], score=float(score), rank=r, source="retriever", score_breakdown=sb))
+        laps.mark("end")
+        self.fast_path_used = True
+        logger.info("[retrieval] dense=%dms bm25=%dms colbert=%dms fuse=%dms graph=%dms rerank=%dms total=%dms "
+                    "enabled(graph=%s,colbert=%s, has_gpu=%s)", laps.ms("start", "dense"), 0, 0, 0, 0, 0, laps.ms("start", "end"),
+                    int(bool(getattr(rcfg, "enable_graph", False))), 0, int(torch.cuda.is_available()))
+        return out
+
     # ------------------------------------------------------------------ batched throughput path
     def search_batch(self, questions: Sequence[str], top_k: int = 10) -> List[List[RetrievalHit]]:
         """Every question through every enabled channel in one launch per channel, fused on the device.
         Requires the three stores to index the same chunk list in the same order (what scripts.build_index
-        produces); otherwise falls back to per-question `search`."""
+        produces); otherwise, or when a reranker is configured, falls back to per-question `search`.  Graph expansion
+        needs a routing decision per question (hybrid_retriever.py:315) and is therefore not part of the batch entry
+        point; the hits carry the fusion method only, not the per-channel breakdown of `search`."""
         rcfg = self.cfg.retrieval
         top_k = max(1, int(top_k))
         eff = max(top_k, int(getattr(rcfg, "top_k", top_k * 8) or (top_k * 8)))
-        self.dense.store.load()
-        self.bm25.load()
-        chunks = self.dense.store.chunks
-        aligned = len(chunks) == len(self.bm25.chunks) and all(a.id == b.id for a, b in zip(chunks, self.bm25.chunks))
-        if aligned and self.colbert is not None:
-            p2c = self.colbert._pid2chunk
-            aligned = len(p2c) == len(chunks) and all(p2c.get(i) is not None and p2c[i].id == c.id for i, c in enumerate(chunks))
-        if not aligned:
+        chunks = self.dense.store.chunks if self._stores_aligned() else None
+        if chunks is None or (getattr(rcfg, "enable_rerank", False) and self.reranker is not None):
+            # stores that index different chunk lists, or a reranker to apply: the per-question path does all of it
             return [self.search(q, None, top_k) for q in questions]
         k = min(eff, len(chunks), engine.LRAG_MAX_K)
         store = self.dense.store

@@ -128,7 +128,12 @@ class VectorStore:
         if self.index is not None and self.chunks and self._index_mtime == index_mtime and self._meta_mtime == meta_mtime:
             return
         with self._load_lock:
-            X, _info = artifacts.read_faiss_index(self.index_path)
+            X, info = artifacts.read_faiss_index(self.index_path)
+            if info.get("metric", artifacts.METRIC_INNER_PRODUCT) != artifacts.METRIC_INNER_PRODUCT:
+                # the reference builds inner-product indexes only (builders/faiss_builder.py:84); scanning an L2 index as
+                # inner product would silently rank by the wrong measure
+                raise ValueError(f"{self.index_path}: FAISS metric_type {info.get('metric')} is not METRIC_INNER_PRODUCT; "
+                                 "this engine scans inner-product indexes only")
             index = GpuFlatIndex.from_numpy(X, self.device if self.device.type == "cuda" else None)
             chunks = artifacts.read_meta_jsonl(self.meta_path)
             # one snapshot, swapped in after it is complete (readers never see a half-loaded store)

@@ -61,6 +61,43 @@ def test_dense_config1_full_size(eng):
     assert torch.equal(mi, i[:256]) and torch.equal(ms, s[:256])
 
 
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("ragged", [False, True])
+def test_maxsim_config2_full_size(eng, ragged):
+    """configs[2]: 1M docs x 128 tokens x 128-d token store (32.8 GB), 1024 queries x 32 tokens, 1000 candidates each -> top-100
+    (colbert_retriever.py:152, 174-182); `ragged` draws document lengths from U{32..128} to exercise the masking.  The
+    literal oracle cannot hold the store; the check is a plain torch fp32 restatement of the same arithmetic on the device
+    for 32 queries spread over the batch, plus sortedness and a repeat run."""
+    from legal_rag_b200 import synth
+    Nd, Ld, Lq, nq, C, k = 1_000_000, 128, 32, 1024, 1000, 100
+    D = synth.unit_tokens_bf16(Nd, Ld, 128, 5, "cuda")
+    Q = synth.unit_tokens_bf16(nq, Lq, 128, 7, "cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    cand = torch.argsort(torch.rand((nq, 4 * C), generator=g, device="cuda"), dim=1)[:, :C]            # distinct per row ...
+    cand = (cand * (Nd // (4 * C)) + torch.randint(0, Nd // (4 * C), (nq, C), generator=g, device="cuda")).long()   # ... over the store
+    cand[5, 17] = -1                                                                                     # a skipped slot
+    doclen = None
+    if ragged:
+        g6 = torch.Generator(device="cuda"); g6.manual_seed(6)
+        doclen = torch.randint(32, Ld + 1, (Nd,), generator=g6, device="cuda", dtype=torch.int32)
+    s, i = eng.maxsim_rerank(D, doclen, Q, cand, k)
+    _rows_sorted_and_unique(s, i)
+    s2, i2 = eng.maxsim_rerank(D, doclen, Q, cand, k)
+    assert torch.equal(i, i2) and torch.equal(s, s2), "second run differs"
+    sub = list(range(0, nq, nq // 32))[:32]
+    ref_s = torch.full((len(sub), C), float("-inf"), device="cuda")
+    for n, q in enumerate(sub):
+        rows = cand[q]
+        ok = rows >= 0
+        sim = torch.einsum("ld,ctd->clt", Q[q].float(), D[rows[ok]].float())                            # [c, Lq, Ld]
+        if doclen is not None:
+            sim = sim.masked_fill(torch.arange(Ld, device="cuda")[None, None, :] >= doclen[rows[ok]].long()[:, None, None], -9999.0)
+        ref_s[n, ok] = sim.amax(2).sum(1)
+    o = torch.argsort(ref_s, dim=1, descending=True, stable=True)[:, :k + 20]
+    check_topk_parity(s[sub].cpu().numpy(), i[sub].cpu().numpy(), torch.gather(ref_s, 1, o).cpu().numpy(),
+                      torch.gather(cand[sub], 1, o).cpu().numpy(), k, 1e-4, what=f"maxsim-1M-ragged{int(ragged)}", floor=1.0)
+
+
 def _torch_bm25_reference(index, q_indptr, q_term, rows, k):
     """fp64 scatter-add of `multiplicity * impact` over the posting lists of each query, then top-k by
     (score desc, id asc) -- the reference's get_scores + stable sort, evaluated on the device."""

@@ -104,6 +104,44 @@ def test_topk_merge_matches_oracle(eng):
     assert (i[:, 10:] == -1).all() and (i[:, :10] >= 0).all()
 
 
+def test_merge_and_select_keep_64_bit_ids(eng):
+    """Ids beyond 2^32 (and rows whose ids span more than 2^32) come back whole from the merge, the in-place shard merge
+    and the column-id select: they never pass through the 32-bit tie field of the selection keys (round-1 finding)."""
+    rng = np.random.default_rng(12)
+    nq, G, k = 5, 4, 50
+    sc = rng.standard_normal((nq, G * k)).astype(np.float32)
+    big = (1 << 33) + 5
+    # narrow rows far above 2^32, and wide rows that mix small and huge ids
+    ids_narrow = big + np.stack([rng.permutation(10 ** 6)[:G * k] for _ in range(nq)]).astype(np.int64)
+    ids_wide = ids_narrow.copy()
+    ids_wide[:, ::3] -= big
+    for ids in (ids_narrow, ids_wide):
+        ids = ids.copy()
+        ids[:, -9:] = -1
+        sc2 = sc.copy()
+        sc2[:, 3] = sc2[:, 4] = sc2[:, 5]                    # a three-way tie: ascending id order, whatever the width
+        s, i = eng.topk_merge(torch.from_numpy(sc2).cuda(), torch.from_numpy(ids).cuda(), k)
+        D, I = odense.merge_topk(sc2, ids, k)
+        np.testing.assert_array_equal(i.cpu().numpy(), I)
+        np.testing.assert_array_equal(s.cpu().numpy(), D)
+        # the same lists as G shards of k entries, laid out [shard, query, k] like an all-gather leaves them
+        gs = torch.from_numpy(np.ascontiguousarray(sc2.reshape(nq, G, k).transpose(1, 0, 2))).cuda()
+        gi = torch.from_numpy(np.ascontiguousarray(ids.reshape(nq, G, k).transpose(1, 0, 2))).cuda()
+        s, i = eng.topk_merge_shards(gs, gi, k)
+        np.testing.assert_array_equal(i.cpu().numpy(), I)
+        np.testing.assert_array_equal(s.cpu().numpy(), D)
+    # column ids of the select (MaxSim candidate ranking): short rows and streamed long rows
+    for N in (300, 200_000):
+        S = rng.standard_normal((3, N)).astype(np.float32)
+        cid = big * 3 + np.stack([rng.permutation(N) for _ in range(3)]).astype(np.int64) * 7
+        cid[:, 5] = -1
+        s, i = eng.topk_select(torch.from_numpy(S).cuda(), 40, col_id=torch.from_numpy(cid).cuda())
+        Sm = np.where(cid >= 0, S, -np.inf)
+        order = np.argsort(-Sm, axis=1, kind="stable")[:, :40]
+        np.testing.assert_array_equal(i.cpu().numpy(), np.take_along_axis(cid, order, 1))
+        np.testing.assert_array_equal(s.cpu().numpy(), np.take_along_axis(S, order, 1))
+
+
 # ---------------------------------------------------------------- dense
 DENSE_SHAPES = [
     # (N, d, nq, k)

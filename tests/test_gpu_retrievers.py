@@ -143,6 +143,40 @@ def test_search_batch_equals_per_question_search(world):
                           np.array([[h.score for h in one]]), np.array([[row[h.chunk.id] for h in one]]), len(one), 1e-3, what="cls-batch")
 
 
+@pytest.mark.parametrize("method", ["rrf_norm_blend", "weighted_sum"])
+def test_search_fast_path_equals_general_path(world, method):
+    """Without a ColBERT channel / graph / reranker, search() answers a question with one captured CUDA graph
+    (HybridRetriever._search_graphed); the hits, scores and score_breakdown are those of the general per-channel path."""
+    import copy
+    from legal_rag_b200.retrieval import HybridRetriever
+    cfg = copy.deepcopy(world["cfg"])
+    cfg.retrieval.enable_colbert = False
+    cfg.retrieval.fusion_method = method
+    cfg.retrieval.top_k = 50
+    cfg.retrieval.min_final_score = 0.05
+    fast, slow = HybridRetriever(cfg), HybridRetriever(cfg)
+    slow._search_graphed = lambda *a, **k: None
+    for qn in QUESTIONS:
+        for top_k in (10, 50):
+            a, b = fast.search(qn, None, top_k), slow.search(qn, None, top_k)
+            assert fast.fast_path_used and not slow.fast_path_used
+            assert len(a) == len(b) > 0
+            sa = {h.chunk.id: h for h in a}
+            for hb in b:
+                ha = sa.get(hb.chunk.id)
+                if ha is None:                       # only a tie at the cut may differ
+                    assert abs(hb.score - b[-1].score) < 1e-6
+                    continue
+                assert abs(ha.score - hb.score) < 1e-6
+                assert ha.source == hb.source == "retriever"
+                assert set(ha.score_breakdown) == set(hb.score_breakdown)
+                assert sorted(ha.score_breakdown["channel"]) == sorted(hb.score_breakdown["channel"])
+                for key in ("rrf_norm", "weighted_sum", "dense_norm", "bm25_norm"):
+                    assert abs(ha.score_breakdown[key] - hb.score_breakdown[key]) < 1e-6
+            assert [h.rank for h in a] == list(range(1, len(a) + 1))
+            assert all(x.score >= y.score for x, y in zip(a, a[1:]))
+
+
 def test_incremental_add_is_searchable_and_persisted(world):
     from legal_rag_b200.retrieval import VectorStore, artifacts, builders
     from legal_rag_b200.schemas import LawChunk

@@ -345,8 +345,13 @@ def test_transformers_colbert_encoder_restates_the_checkpoint_pipeline(tmp_path)
              + ["buyer", "seller", "goods", "contract", "sale", "of", "the", "a"])
     d = tmp_path / "ckpt"
     d.mkdir()
-    (d / "vocab.txt").write_text("\n".join(vocab), encoding="utf-8")
-    BertTokenizerFast(vocab_file=str(d / "vocab.txt")).save_pretrained(d)
+    from tokenizers import Tokenizer, models, normalizers, pre_tokenizers, processors
+    wp = Tokenizer(models.WordPiece({w: i for i, w in enumerate(vocab)}, unk_token="[UNK]"))
+    wp.normalizer = normalizers.BertNormalizer(lowercase=True)
+    wp.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
+    wp.post_processor = processors.BertProcessing(("[SEP]", vocab.index("[SEP]")), ("[CLS]", vocab.index("[CLS]")))
+    BertTokenizerFast(tokenizer_object=wp, unk_token="[UNK]", pad_token="[PAD]", cls_token="[CLS]", sep_token="[SEP]",
+                      mask_token="[MASK]").save_pretrained(d)
     torch.manual_seed(1)
     bert = BertModel(BertConfig(vocab_size=len(vocab), hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
                                 max_position_embeddings=64))
