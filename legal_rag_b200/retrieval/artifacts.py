@@ -22,7 +22,7 @@ import struct
 import sys
 import types
 from pathlib import Path
-from typing import Any, Dict, List, Tuple
+from typing import Optional, Any, Dict, List, Tuple
 
 import numpy as np
 
@@ -80,8 +80,9 @@ def _read_flat(r: _Reader) -> Tuple[np.ndarray, Dict[str, Any]]:
     return xb.reshape(h["ntotal"], h["d"]), h
 
 
-def read_faiss_index(path) -> Tuple[np.ndarray, Dict[str, Any]]:
-    """-> (float32 [ntotal, d] vectors in id order, info dict with d / ntotal / metric / fourcc / hnsw)."""
+def read_faiss_index(path, with_graph: bool = False) -> Tuple[np.ndarray, Dict[str, Any]]:
+    """-> (float32 [ntotal, d] vectors in id order, info dict with d / ntotal / metric / fourcc / hnsw).  `with_graph`
+    keeps the HNSW arrays (levels, offsets, neighbors, ...) in info["hnsw"] instead of only its scalars."""
     buf = Path(path).read_bytes()
     r = _Reader(buf)
     fourcc = buf[:4]
@@ -106,7 +107,7 @@ def read_faiss_index(path) -> Tuple[np.ndarray, Dict[str, Any]]:
         except ValueError:
             X, h = _locate_nested_flat(buf, outer)
             hn = {}
-        h["hnsw"] = {k: (v if np.isscalar(v) else None) for k, v in hn.items()}
+        h["hnsw"] = {k: (v if (with_graph or np.isscalar(v)) else None) for k, v in hn.items()}
         h["outer_fourcc"] = fourcc.decode()
         return X, h
     raise ValueError(f"faiss index {path}: unsupported index type {fourcc!r} (flat and HNSW-flat files are supported)")
@@ -141,21 +142,64 @@ def write_faiss_flat(path, X: np.ndarray, metric: int = METRIC_INNER_PRODUCT) ->
     os.replace(tmp, path)
 
 
-def write_faiss_hnsw_flat(path, X: np.ndarray, M: int = 64, ef_construction: int = 400, ef_search: int = 512) -> None:
-    """IndexHNSWFlat-shaped file with an EMPTY graph around the flat storage: enough for this engine (which
-    ignores the graph) and for tests of the HNSW reader; a real faiss would need the graph rebuilt."""
+def knn_graph(X: np.ndarray, m: int, block: int = 2048) -> np.ndarray:
+    """Exact inner-product m-nearest-neighbour lists [n, m] (self excluded, -1 padded) on the host: the level-0 links of
+    the HNSW container below for corpora small enough for numpy (builders.build_faiss_index computes them with the dense
+    scan kernel instead when a GPU is there)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    n = X.shape[0]
+    out = np.full((n, m), -1, dtype=np.int32)
+    kk = min(m, max(n - 1, 0))
+    if kk == 0:
+        return out
+    for lo in range(0, n, block):
+        S = X[lo:lo + block] @ X.T
+        S[np.arange(S.shape[0]), np.arange(lo, lo + S.shape[0])] = -np.inf          # no self links
+        idx = np.argpartition(-S, kk - 1, axis=1)[:, :kk]
+        order = np.argsort(-np.take_along_axis(S, idx, 1), axis=1, kind="stable")
+        out[lo:lo + S.shape[0], :kk] = np.take_along_axis(idx, order, 1)
+    return out
+
+
+def write_faiss_hnsw_flat(path, X: np.ndarray, M: int = 64, ef_construction: int = 400, ef_search: int = 512,
+                          neighbors: Optional[np.ndarray] = None) -> None:
+    """IndexHNSWFlat file (builders/faiss_builder.py:84-96 writes this type) [upstream faiss write_index: fourcc IHNf, index
+    header, HNSW {assign_probas, cum_nneighbor_per_level, levels, offsets, neighbors, entry_point, max_level, efConstruction,
+    efSearch, upper_beam}, nested IndexFlat].  The graph is a single-level HNSW: every vector sits on level 0 only
+    (levels[i] = 1), owns 2 M neighbour slots there and links to its exact inner-product nearest neighbours (`neighbors`
+    [n, <= 2 M] int32, -1 = empty; computed on the host when not given), entry point 0.  That is a graph a faiss search can
+    walk (greedy descent is empty, level-0 beam search runs over exact kNN links); this engine itself ignores the graph and
+    scans the flat storage exactly.  The layout follows the published format and has not been opened by a real faiss here
+    (none is installable): parity unpinned."""
     X = np.ascontiguousarray(X, dtype=np.float32)
     n, d = X.shape
+    slots = 2 * M
+    if neighbors is None:
+        neighbors = knn_graph(X, slots) if n <= 50_000 else np.full((n, 0), -1, dtype=np.int32)
+    nb = np.full((n, slots), -1, dtype=np.int32)
+    w = min(slots, neighbors.shape[1])
+    nb[:, :w] = neighbors[:, :w]
+    # faiss HNSW::set_default_probas(M, 1 / ln M): level l is drawn with probability e^(-l / mult) (1 - e^(-1 / mult))
+    mult = 1.0 / np.log(max(M, 2))
+    probas, cum = [], [0]
+    level = 0
+    while True:
+        pr = float(np.exp(-level / mult) * (1 - np.exp(-1 / mult)))
+        if pr < 1e-9:
+            break
+        probas.append(pr)
+        cum.append(cum[-1] + (slots if level == 0 else M))
+        level += 1
     tmp = str(path) + ".tmp"
     with open(tmp, "wb") as f:
         f.write(b"IHNf")
         f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, METRIC_INNER_PRODUCT))
-        for dtype, vals in ((np.float64, [1.0]), (np.int32, [0, 2 * M]), (np.int32, [1] * n), (np.uint64, [0] * (n + 1)),
-                            (np.int32, [])):
+        for dtype, vals in ((np.float64, probas), (np.int32, cum), (np.int32, np.ones(n, dtype=np.int32)),
+                            (np.uint64, np.arange(n + 1, dtype=np.uint64) * np.uint64(slots)), (np.int32, nb.reshape(-1))):
             a = np.asarray(vals, dtype=dtype)
             f.write(struct.pack("<Q", a.size))
             f.write(a.tobytes())
-        f.write(struct.pack("<iiiii", -1, -1, ef_construction, ef_search, 1))
+        f.write(struct.pack("<iiiii", 0 if n else -1, 0 if n else -1, ef_construction, ef_search, 1))
         f.write(b"IxFI")
         f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, METRIC_INNER_PRODUCT))
         f.write(struct.pack("<Q", n * d))

@@ -19,7 +19,8 @@ from .vector_store import VectorStore
 def build_faiss_index(cfg, chunks: Sequence[LawChunk], encoder=None, flat: bool = True) -> None:
     """builders/faiss_builder.py:66-104.  The reference writes IndexHNSWFlat; an exact engine needs only the
     flat storage, so by default a plain IndexFlatIP file is written (the reference's VectorStore.load opens
-    it unchanged: vector_store.py:112-117).  flat=False wraps it in an HNSW container with an empty graph."""
+    it unchanged: vector_store.py:112-117).  flat=False writes the reference's own type, IndexHNSWFlat, with a single-level
+    graph of exact nearest-neighbour links (computed by the dense scan kernel when a GPU is present)."""
     rcfg = cfg.retrieval
     enc = encoder or encoders.make_dense_encoder(str(rcfg.embedding_model), "cpu")
     X = np.asarray(enc.encode([c.text for c in chunks], batch_size=64, max_length=512), dtype=np.float32)
@@ -28,9 +29,30 @@ def build_faiss_index(cfg, chunks: Sequence[LawChunk], encoder=None, flat: bool 
     if flat:
         artifacts.write_faiss_flat(rcfg.faiss_index_file, X)
     else:
-        artifacts.write_faiss_hnsw_flat(rcfg.faiss_index_file, X, int(getattr(rcfg, "hnsw_m", 64)),
-                                        int(getattr(rcfg, "hnsw_ef_construction", 400)), int(getattr(rcfg, "hnsw_ef_search", 512)))
+        M = int(getattr(rcfg, "hnsw_m", 64))
+        artifacts.write_faiss_hnsw_flat(rcfg.faiss_index_file, X, M, int(getattr(rcfg, "hnsw_ef_construction", 400)),
+                                        int(getattr(rcfg, "hnsw_ef_search", 512)), neighbors=_knn_links(X, 2 * M))
     artifacts.write_meta_jsonl(rcfg.faiss_meta_file, chunks)
+
+
+def _knn_links(X: np.ndarray, m: int) -> Optional[np.ndarray]:
+    """Exact inner-product nearest neighbours of every row (self excluded) through the dense scan kernel; None without a GPU
+    (the writer then falls back to numpy for small corpora)."""
+    import torch
+    n = X.shape[0]
+    if not torch.cuda.is_available() or n < 2:
+        return None
+    from .. import engine
+    k = min(m + 1, n, engine.LRAG_MAX_K)
+    Xd = torch.from_numpy(X).cuda().to(torch.bfloat16)
+    out = np.full((n, m), -1, dtype=np.int32)
+    for lo in range(0, n, 4096):
+        _, idx = engine.dense_topk(Xd, Xd[lo:lo + 4096], k)
+        idx = idx.cpu().numpy()
+        for r in range(idx.shape[0]):
+            row = idx[r][(idx[r] != lo + r) & (idx[r] >= 0)][:m]
+            out[lo + r, :len(row)] = row
+    return out
 
 
 def build_bm25_index(cfg, chunks: Sequence[LawChunk], tokenizer=None) -> None:
@@ -95,10 +117,21 @@ class IncrementalDenseBuilder:
             with open(self.store.meta_path, "a", encoding="utf-8") as f:
                 for c in new_chunks:
                     f.write(json.dumps(c.model_dump(), ensure_ascii=False) + "\n")
+            # The file keeps the ORIGINAL fp32 rows (the reference appends fp32 vectors and rewrites its own index object,
+            # incremental_dense_builder.py:60-75): they are read back from the file, not from the bf16 device matrix, so
+            # repeated increments never degrade what the reference would read.  The container type is kept too.
+            old, info = artifacts.read_faiss_index(self.store.index_path)
+            vecs = np.asarray(vecs, dtype=np.float32)
+            full = np.concatenate([old, vecs]) if old.size else vecs
             self.store.index.add(vecs)
             self.store.chunks.extend(new_chunks)
             self.store.index_path.parent.mkdir(parents=True, exist_ok=True)
-            artifacts.write_faiss_flat(self.store.index_path, self.store.index.reconstruct_n())
+            if info.get("hnsw") is not None:
+                M = int(getattr(self.cfg.retrieval, "hnsw_m", 64))
+                artifacts.write_faiss_hnsw_flat(self.store.index_path, full, M, int(getattr(self.cfg.retrieval, "hnsw_ef_construction", 400)),
+                                                int(getattr(self.cfg.retrieval, "hnsw_ef_search", 512)), neighbors=_knn_links(full, 2 * M))
+            else:
+                artifacts.write_faiss_flat(self.store.index_path, full)
             self.store._index_mtime = self.store.index_path.stat().st_mtime
             self.store._meta_mtime = self.store.meta_path.stat().st_mtime
         return len(new_chunks)

@@ -57,6 +57,81 @@ def test_faiss_hnsw_container_is_unwrapped(tmp_path):
         artifacts.read_faiss_index(tmp_path / "ivf.index")
 
 
+def test_faiss_hnsw_file_carries_a_walkable_graph(tmp_path):
+    """The IndexHNSWFlat writer emits a single-level graph of exact nearest-neighbour links (round-1 finding: the graph was
+    empty): levels / offsets / neighbors are consistent with faiss's layout, and a plain level-0 best-first search over the
+    links from the entry point finds the true nearest neighbours."""
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((300, 16)).astype(np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    M = 8
+    p = tmp_path / "hnsw.index"
+    artifacts.write_faiss_hnsw_flat(p, X, M=M, ef_construction=40, ef_search=32)
+    Y, info = artifacts.read_faiss_index(p, with_graph=True)
+    np.testing.assert_array_equal(X, Y)
+    g = info["hnsw"]
+    n, slots = len(X), 2 * M
+    assert g["entry_point"] == 0 and g["max_level"] == 0 and g["efSearch"] == 32 and g["efConstruction"] == 40
+    assert (g["levels"] == 1).all() and len(g["levels"]) == n
+    np.testing.assert_array_equal(g["offsets"], np.arange(n + 1, dtype=np.uint64) * slots)
+    assert g["cum_nneighbor_per_level"][0] == 0 and g["cum_nneighbor_per_level"][1] == slots
+    assert abs(sum(g["assign_probas"]) - 1.0) < 1e-6
+    nb = g["neighbors"].reshape(n, slots)
+    S = X @ X.T
+    np.fill_diagonal(S, -np.inf)
+    want = np.argsort(-S, axis=1, kind="stable")[:, :slots]
+    assert (np.sort(nb, axis=1) == np.sort(want, axis=1)).all()
+    # level-0 beam search over the stored links (what a faiss search does once it is on level 0)
+    def search(q, ef=32, k=5):
+        visited, cand, best = {0}, [(-float(X[0] @ q), 0)], [(float(X[0] @ q), 0)]
+        import heapq
+        while cand:
+            negs, v = heapq.heappop(cand)
+            if len(best) >= ef and -negs < min(best)[0]:
+                break
+            for u in nb[v]:
+                if u >= 0 and u not in visited:
+                    visited.add(int(u))
+                    s_ = float(X[u] @ q)
+                    if len(best) < ef or s_ > min(best)[0]:
+                        heapq.heappush(cand, (-s_, int(u)))
+                        best.append((s_, int(u)))
+                        best = sorted(best, reverse=True)[:ef]
+        return [i for _, i in sorted(best, reverse=True)[:k]]
+    hits = 0
+    for _ in range(20):
+        q = rng.standard_normal(16).astype(np.float32)
+        hits += len(set(search(q)) & set(np.argsort(-(X @ q))[:5].tolist()))
+    assert hits >= 90                                    # recall@5 >= 0.9 over 20 random queries
+
+
+def test_incremental_dense_builder_keeps_fp32_rows_and_the_container_type(tmp_path, monkeypatch):
+    """IncrementalDenseBuilder re-writes the index from the fp32 rows of the FILE plus the new fp32 vectors -- not from the
+    bf16 device matrix (round-1 finding) -- and keeps an HNSW container an HNSW container.  Host logic only: the device
+    index is faked."""
+    from types import SimpleNamespace
+    from legal_rag_b200.retrieval import builders
+    X0 = np.random.default_rng(5).standard_normal((6, 8)).astype(np.float32)
+    idx, meta = tmp_path / "faiss.index", tmp_path / "meta.jsonl"
+    artifacts.write_faiss_hnsw_flat(idx, X0, M=2)
+    chunks = [LawChunk(id=f"c{i}", law_name="L", article_no=str(i), article_id=f"a{i}", text=f"t{i}") for i in range(8)]
+    artifacts.write_meta_jsonl(meta, chunks[:6])
+    added = []
+    new_vecs = np.random.default_rng(6).standard_normal((2, 8)).astype(np.float32)
+    store = SimpleNamespace(chunks=list(chunks[:6]), index_path=idx, meta_path=meta, load=lambda: None,
+                            _embed=lambda texts, is_query=False: new_vecs, index=SimpleNamespace(add=lambda v: added.append(np.array(v))),
+                            _index_mtime=None, _meta_mtime=None)
+    monkeypatch.setattr(builders, "_knn_links", lambda X, m: None)
+    cfg = SimpleNamespace(retrieval=SimpleNamespace(faiss_index_file=str(idx), hnsw_m=2, hnsw_ef_construction=40, hnsw_ef_search=16))
+    b = builders.IncrementalDenseBuilder(cfg, store=store)
+    assert b.add_chunks(chunks) == 2 and len(added) == 1
+    Y, info = artifacts.read_faiss_index(idx, with_graph=True)
+    np.testing.assert_array_equal(Y, np.concatenate([X0, new_vecs]))            # bit-identical fp32 rows, old and new
+    assert info["outer_fourcc"] == "IHNf" and len(info["hnsw"]["levels"]) == 8
+    assert len(artifacts.read_meta_jsonl(meta)) == 8
+    assert b.add_chunks(chunks) == 0                                             # nothing new: no rewrite
+
+
 def test_meta_jsonl_roundtrip(tmp_path):
     cs = _chunks(5)
     artifacts.write_meta_jsonl(tmp_path / "m.jsonl", cs)
