@@ -44,9 +44,10 @@ def measured_traffic(kernel: str, **shape):
     this workload shape; otherwise null."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            entry = json.load(f).get(kernel)
-        if entry and all(entry["shape"].get(k) == v for k, v in shape.items()):
-            return entry["dram_bytes_per_step"]
+            entries = json.load(f).get(kernel) or []
+        for entry in entries if isinstance(entries, list) else [entries]:
+            if all(entry["shape"].get(k) == v for k, v in shape.items()):
+                return entry["dram_bytes_per_step"]
     except (OSError, ValueError, KeyError):
         pass
     return None
@@ -154,12 +155,19 @@ class DenseWorkload:
 
     def roofline(self, kernel_ms, peaks):
         flops = 2.0 * self.nq * self.N * self.d
+        scan_gbs = self.N * self.d * 2 / (kernel_ms * 1e-3) / 1e9
+        if self.nq < 216:
+            # below the ridge point (216 FLOP per corpus byte) the scan is bound by reading the corpus once
+            return {"bound": "hbm", "achieved": scan_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": scan_gbs / peaks["hbm_gbs"],
+                    "traffic": None, "kernel": "dense_scan_kernel", "kernel_ms": kernel_ms,
+                    "algorithmic": f"2*N*d = {2.0 * self.N * self.d:.3e} B per step (the corpus, once)", "peak_source": peaks["source"] + " (copy bandwidth)",
+                    "scan_gbs": scan_gbs}
         ach = flops / (kernel_ms * 1e-3) / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 "traffic": measured_traffic("dense_scan_kernel", N=self.N, d=self.d, nq=self.nq, k=self.k),
                 "kernel": "dense_scan_kernel", "kernel_ms": kernel_ms,
                 "algorithmic": f"2*nq*N*d = {flops:.3e} FLOP per launch", "peak_source": peaks["source"] + " (sustained cuBLAS bf16)",
-                "scan_gbs": self.N * self.d * 2 / (kernel_ms * 1e-3) / 1e9}
+                "scan_gbs": scan_gbs}
 
     # ---- CPU leg: oracle flat-IP (numpy fp32 BLAS + exact top-k) on a bounded sample ----
     def cpu_sample(self, budget_s=15.0):

@@ -29,10 +29,17 @@ constexpr int SC_KB = SC_DIM / SC_BK;
 constexpr int SC_STAGES = 3;          // doc tiles in flight (a stage = one whole 256 x 128 doc tile, 64 KB)
 constexpr int SC_A_BYTES = SC_BM * SC_DIM * 2;        // 32 KB: the CTA's query block, resident for a whole pass
 constexpr int SC_B_BYTES = SC_BN * SC_DIM * 2;        // 64 KB
-constexpr int SC_EPI_WARPS = 8;       // two per TMEM lane quadrant, each takes half of the tile's columns
-constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int SC_PART_BYTES = 2 * 4 * 32 * 4;         // partial maxima exchanged when Ld = 256
+#ifndef LRAG_SCAN_EPI_PER_QUAD
+#define LRAG_SCAN_EPI_PER_QUAD 2
+#endif
+constexpr int SC_EPQ = LRAG_SCAN_EPI_PER_QUAD;        // epilogue warps per TMEM lane quadrant; each takes 256 / SC_EPQ columns of the tile
+constexpr int SC_EPI_WARPS = 4 * SC_EPQ;
+constexpr int SC_THREADS = 64 + 32 * SC_EPI_WARPS;    // warp0 TMA, warp1 MMA, the rest epilogue
+constexpr int SC_WCOLS = SC_BN / SC_EPQ;              // columns per epilogue warp
+constexpr int SC_WCHUNKS = SC_WCOLS / 32;             // 32-column TMEM loads per epilogue warp and tile
+constexpr int SC_PART_BYTES = 4 * (SC_EPQ - 1) * 32 * 4;  // partial maxima of the warps that do not finish their document (the last warp of a quadrant never hands one over)
 constexpr int SC_SMEM = SC_A_BYTES + SC_STAGES * SC_B_BYTES + 1024 /*align*/ + 256 /*barriers*/ + SC_PART_BYTES;
+static_assert(SC_SMEM <= 227 * 1024, "the tiles, barriers and partial maxima must fit one CTA's shared memory");
 constexpr float SC_PAD_FILL = -9999.0f;   // value of a masked (padding) doc token, as in maxsim.cu / the oracle
 
 struct ScanParams {
@@ -65,7 +72,7 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* afull_bar = bars + 2 * SC_STAGES + 4;  // query block landed
   uint64_t* aempty_bar = bars + 2 * SC_STAGES + 5; // last MMA of the pass retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SC_STAGES + 6);
-  float* part = reinterpret_cast<float*>(smem_b + SC_STAGES * SC_B_BYTES + 256);   // [2 buffers][4 quads][32 lanes]
+  float* part = reinterpret_cast<float*>(smem_b + SC_STAGES * SC_B_BYTES + 256);   // [4 quads][SC_EPQ - 1 warps][32 lanes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -152,11 +159,27 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
   } else {
     // ===================== epilogue: max over a document's tokens, sum over the query's tokens =====
-    // Two warps per TMEM lane quadrant (= query inside the block); each takes one half of the tile's
-    // columns.  With Ld = 256 the single document spans both halves: the partial maxima meet in smem.
+    // SC_EPQ warps per TMEM lane quadrant (= query inside the block); warp `slot` of a quadrant takes columns
+    // [slot * SC_WCOLS, (slot + 1) * SC_WCOLS) of the tile.  A document longer than that spans several warps: their partial
+    // maxima meet in shared memory and the warp that holds the document's last columns finishes it.
+    // tools/micro/tmem_ld.cu: tcgen05.ld delivers 730-940 B/clk/SM to 8-16 reader warps, 6-7x what this epilogue needs; its
+    // cost is the dependent max chains, which is why it is spread over 16 warps (4 per scheduler).
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int slot = (warp - 2) >> 2;
     const int dpt = SC_BN / p.Ld;                  // documents per tile
+    const int span = p.Ld > SC_WCOLS ? p.Ld / SC_WCOLS : 1;      // warps that share one document
+    const int quad_bar = quad + 1;                 // named barrier of the quadrant's warps
+    // which document of the tile, and which of its tokens, each of this warp's 32-column chunks holds: the same for every
+    // tile (Ld is a power of two: 32, 64, 128 or 256)
+    const int c0 = slot * SC_WCHUNKS;
+    const int ld_shift = 31 - __clz(p.Ld);
+    int off_c[SC_WCHUNKS], din_c[SC_WCHUNKS];
+#pragma unroll
+    for (int i = 0; i < SC_WCHUNKS; ++i) {
+      const int col = (c0 + i) * 32;
+      din_c[i] = col >> ld_shift;
+      off_c[i] = col & (p.Ld - 1);
+    }
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
       const int qb = int(u % p.QB);
@@ -176,51 +199,51 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
         float m = SC_PAD_FILL;
-        // the next chunk's TMEM load is in flight while this one is reduced
+        // the next chunk's TMEM load is in flight while this one is reduced.  (Requesting all of a warp's columns at once and
+        // waiting once was measured: 86.5 ms against 67.1 ms for 64 queries x 1M documents -- 128 live registers of loaded
+        // values cost more than the overlap gains.)
         uint32_t v[2][32];
-        const int c0 = half * (SC_BN / 64);
-        int dl_c[SC_BN / 64], off_c[SC_BN / 64], din_c[SC_BN / 64];
+        int dl_c[SC_WCHUNKS];
 #pragma unroll
-        for (int i = 0; i < SC_BN / 64; ++i) {
-          const int col = (c0 + i) * 32;
-          din_c[i] = col / p.Ld;
-          off_c[i] = col - din_c[i] * p.Ld;
-          dl_c[i] = p.debug == 1 ? 0 : __shfl_sync(0xffffffffu, dl_mine, din_c[i]);
-        }
+        for (int i = 0; i < SC_WCHUNKS; ++i) dl_c[i] = p.debug == 1 ? 0 : __shfl_sync(0xffffffffu, dl_mine, din_c[i]);
         if (off_c[0] < dl_c[0]) tmem_ld_32x32(taddr + c0 * 32, v[0]);
 #pragma unroll
-        for (int i = 0; i < SC_BN / 64; ++i) {
+        for (int i = 0; i < SC_WCHUNKS; ++i) {
           const int c = c0 + i;
           const int din = din_c[i], off = off_c[i], dl = dl_c[i];
           tmem_ld_wait();
-          if (i + 1 < SC_BN / 64 && off_c[i + 1 < SC_BN / 64 ? i + 1 : i] < dl_c[i + 1 < SC_BN / 64 ? i + 1 : i])
+          if (i + 1 < SC_WCHUNKS && off_c[i + 1 < SC_WCHUNKS ? i + 1 : i] < dl_c[i + 1 < SC_WCHUNKS ? i + 1 : i])
             tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
           if (off < dl) {                            // warp-uniform: the chunk holds unmasked tokens
             const uint32_t* vv = v[i & 1];
             if (off + 32 <= dl) {
-              float m4[4];
+              // 32 values -> 1 through three-input maxima (FMNMX3): 16 instructions in 4 dependent levels
+              float l1[11];
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float x = __uint_as_float(vv[g * 8]);
-#pragma unroll
-                for (int j = 1; j < 8; ++j) x = fmaxf(x, __uint_as_float(vv[g * 8 + j]));
-                m4[g] = x;
-              }
-              m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+              for (int g = 0; g < 10; ++g)
+                l1[g] = fmaxf(fmaxf(__uint_as_float(vv[3 * g]), __uint_as_float(vv[3 * g + 1])), __uint_as_float(vv[3 * g + 2]));
+              l1[10] = fmaxf(__uint_as_float(vv[30]), __uint_as_float(vv[31]));
+              const float a0 = fmaxf(fmaxf(l1[0], l1[1]), l1[2]), a1 = fmaxf(fmaxf(l1[3], l1[4]), l1[5]);
+              const float a2 = fmaxf(fmaxf(l1[6], l1[7]), l1[8]), a3 = fmaxf(fmaxf(l1[9], l1[10]), m);
+              m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
                 if (off + j < dl) m = fmaxf(m, __uint_as_float(vv[j]));
             }
           }
-          const bool doc_ends = off + 32 == p.Ld;
-          const bool half_ends = p.Ld == SC_BN && c == SC_BN / 64 - 1;     // first half of a 256-token document
-          if (half_ends) {
-            part[(as * 4 + quad) * 32 + lane] = m;   // handed to the warp that owns the second half
+          const bool doc_ends = off + 32 == p.Ld;                                   // the document's last columns are in this chunk
+          const bool mine_ends = i == SC_WCHUNKS - 1 && !doc_ends && span > 1;       // my columns end inside a longer document
+          if (mine_ends) {
+            // One partial slot per warp (shared memory is full: 227 KB of tiles).  The previous tile's partial is read by its
+            // finisher before that warp hands the previous accumulator back, so "every epilogue warp has drained the previous
+            // tile" (the accumulator's empty barrier) is what makes the slot free.
+            if (it > 0) mbar_wait(&tempty_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+            part[(quad * (SC_EPQ - 1) + slot) * 32 + lane] = m;                           // handed to the warp that finishes the document
           } else if (doc_ends) {
-            if (p.Ld == SC_BN) {
-              asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");     // partner's partial maximum is in smem
-              m = fmaxf(m, part[(as * 4 + quad) * 32 + lane]);
+            if (span > 1) {
+              asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");   // the partners' partial maxima are in smem
+              for (int s2 = slot - span + 1; s2 < slot; ++s2) m = fmaxf(m, part[(quad * (SC_EPQ - 1) + s2) * 32 + lane]);
             }
             float sum = (lane < p.Lq) ? m : 0.f;
 #pragma unroll
@@ -230,7 +253,8 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             m = SC_PAD_FILL;
           }
         }
-        if (p.Ld == SC_BN && half == 0) asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+        // a warp that only handed a partial over still meets the quadrant's barrier (once per tile, every warp)
+        if (span > 1 && (slot % span) != span - 1) asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
