@@ -133,7 +133,8 @@ int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q
  * BM25 channel.  Replaces `bm25.get_scores(tokens)` + the full Python sort at
  * legalrag/retrieval/bm25_retriever.py:74-75 (rank_bm25.BM25Okapi).
  * Index = term-major CSR with doc ids ascending inside each term:
- *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard), impact [nnz] fp32, both 16-byte aligned
+ *   indptr [V+1] int64, doc_id [nnz] int32 (LOCAL row in this shard), impact [nnz] fp32 (4-byte aligned; 128-byte
+ *   alignment of both arrays keeps every warp-wide load on one line)
  *   = idf[t] * tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl))  with GLOBAL idf/avgdl.
  * Queries = CSR of term ids: q_indptr [nq+1] int64, q_term [*] int32 (repeats allowed and
  * scored once per occurrence, -1 / out-of-range = OOV).
@@ -149,15 +150,26 @@ int lrag_dense_gather_scores_bf16(const void* X, int64_t N, int d, const void* Q
  * an 8-token query with impacts up to 30 -- which makes the sums exact, order-independent and
  * reproducible; a bound that is too small lets a score overflow. */
 size_t lrag_bm25_topk_workspace_bytes(int64_t N, int nq, int k, int64_t max_query_terms);
-/* Tuning knob (process-wide; call before sizing the workspace): documents per work item =
- * slabs * 12288.  Small items keep the posting ranges all queries are working on inside L2;
- * large items amortise the per-item state hand-off.  0 restores the default (32, or the
- * LRAG_BM25_ITEM_SLABS environment variable). */
+/* Tuning knob (process-wide; set it once, before sizing workspaces and not concurrently with launches): slabs per
+ * work item (a slab is the doc range one CTA accumulates in shared memory: 22 528 docs for k <= 256).  Small items
+ * keep the posting ranges all queries are working on inside L2; large items amortise the per-item state hand-off.
+ * 0 restores the default (about 393 k docs per item, or the LRAG_BM25_ITEM_SLABS environment variable). */
 int lrag_bm25_set_item_slabs(int slabs);
 int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V,
                    int64_t nnz, const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                    int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
                    int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
+/* The same with DENSE ROWS for the few terms that occur in most documents (under Zipf two or three terms carry most of
+ * the posting volume): dense_term [n_dense] int32 ascending term ids, dense_rows [n_dense, dense_stride] fp32 with
+ * dense_rows[r, d] = impact of term dense_term[r] in LOCAL doc d (0 where absent), dense_stride >= N a multiple of
+ * 32, rows 128-byte aligned.  Such a term is walked by doc range instead of by (doc, impact) pairs: half the bytes at
+ * density > 0.5, no doc ids, conflict-free accumulator updates.  Results are those of lrag_bm25_topk (a posting whose
+ * impact is exactly 0 contributes nothing either way); the postings of those terms stay in the CSR (they define df). */
+int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
+                         const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
+                         const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                         int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
+                         int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * ColBERT channel.  Replaces the scoring inside `Searcher.search(query, k)` at

@@ -44,6 +44,8 @@ SIGNATURES = {
     "lrag_bm25_set_item_slabs": (_c_int, [_c_int]),
     "lrag_bm25_topk": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_int, _c_i64, _c_int,
                                 C.c_float, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "lrag_bm25_topk_dense": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_int,
+                                      _c_i64, _c_int, C.c_float, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_maxsim_rerank_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "lrag_maxsim_rerank_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_p, _c_int, _c_int,
                                          _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),

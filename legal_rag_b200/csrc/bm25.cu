@@ -74,18 +74,28 @@ constexpr int BM25_SEG = LRAG_BM25_SEG;              // postings per segment des
 constexpr int BM25_SEG_PER_LANE = BM25_SEG / 32;
 constexpr int BM25_TABS = 4;                         // slab tables in flight
 constexpr int BM25_WARPS = BM25_CONSUMERS / 32;
-constexpr int BM25_HOT = 512;                        // docs per slab whose running score reached the threshold (more: full scan)
+constexpr int BM25_HOT = 256;                        // docs per slab whose running score reached the threshold (more: full scan)
 constexpr int BM25_BAR_CONSUMERS = 1;                // named barrier id of the consumer warps
 constexpr int BM25_KEEP = 2 * LRAG_MAX_K / BM25_CONSUMERS;   // candidate keys a thread may hold across a compaction
 constexpr int BM25_DEFAULT_ITEM_DOCS = 32 * 12288;   // docs per work item (the item is a whole number of slabs)
-enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16 };
+constexpr int BM25_DENSE_FLAG = 1 << 30;             // in a slab table's run count: the run is a doc range of a dense row
+enum : int { BM25_F_SLAB_END = 1, BM25_F_ITEM_BEGIN = 2, BM25_F_ITEM_END = 4, BM25_F_FINAL = 8, BM25_F_END = 16, BM25_F_SLAB_BEGIN = 32 };
+
+#ifdef LRAG_BM25_TIMING
+// Debug build only (tools/gpu_bm25_timing.py): warp-cycles the consumer warps spend per phase, summed over the grid.
+__device__ unsigned long long g_bm25_t[16];    // table wait, slab init, chunk loop, slab end, item begin/end, tables, chunks, slabs
+__device__ long long g_bm25_trace[1024 * 16 * 4];   // block 0, first 1024 slabs, per consumer warp: chunk loop begin / end, chunks, barrier passed
+#define BM25_T(i, expr) do { const long long t_ = clock64(); expr; tacc[i] += clock64() - t_; } while (0)
+#else
+#define BM25_T(i, expr) do { expr; } while (0)
+#endif
 
 struct Bm25Ws {
   unsigned long long* counter;     // next item
   int* cur_flag;                   // [nc] steps whose final term cursors are published
   int* cand_flag;                  // [nc] steps whose candidate state is published
   int* q_nt;                       // [nq] distinct in-vocabulary terms with postings
-  int64_t* tq_start;               // [nq, TS] first posting
+  int64_t* tq_start;               // [nq, TS] first posting; -(r + 1) = dense row r
   int32_t* tq_len;                 // [nq, TS] df
   float* tq_mult;                  // [nq, TS] occurrences in the query x the query's fixed-point scale
   float* q_inv_scale;              // [nq] 1 / scale
@@ -99,6 +109,11 @@ struct Bm25Ws {
 struct Bm25Params {
   const int64_t* indptr; const int32_t* doc_id; const float* impact; int64_t V; int64_t nnz;
   const int64_t* q_indptr; const int32_t* q_term;
+  // Dense rows: for the few terms that occur in most documents, impact[d] for EVERY doc of the shard (0 where the term is
+  // absent), n_dense rows of dense_stride floats (a multiple of 32).  A dense term's "posting list" is the doc range
+  // itself: half the bytes of (doc, impact) pairs at density > 0.5, no doc ids to load, and consecutive lanes add into
+  // consecutive accumulators (no bank conflicts).
+  const int32_t* dense_term; const float* dense_rows; int n_dense; int64_t dense_stride;
   int64_t N; int64_t dps;          // docs per split (multiple of the item size)
   unsigned long long total_items;
   int nq, k, nonneg, S, cap, P, TS, item_slabs, steps, nc;
@@ -132,8 +147,9 @@ struct alignas(16) Bm25Tab {
 struct Bm25Shared {
   SelectShared sel;
   Bm25Tab tab[BM25_TABS];
-  int hot[BM25_HOT];               // docs of the current slab whose running score reached the threshold
-  int hot_cnt;
+  int hot[2][BM25_HOT];            // docs of the current slab whose running score reached the threshold (buffer = slab parity)
+  int hot_cnt[2];
+  int drained;                     // last slab whose hot docs warp 0 has read out of the accumulators
   uint64_t bfull_bar[2], bempty_bar[2];                      // group buffers
   Bm25Group grp[2];
   int64_t t_start[BM25_MAXT];      // bounds warp's view of the current item's query
@@ -310,8 +326,12 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
       const uint32_t m = __ballot_sync(0xffffffffu, own);
       if (own) {
         const size_t slot = size_t(q) * p.TS + base + __popc(m & ((1u << lane) - 1));
-        p.ws.tq_start[slot] = s;
-        p.ws.tq_len[slot] = int32_t(e - s);
+        // a term with a dense row is walked by doc range instead of by postings
+        int lo_r = 0, hi_r = p.n_dense;
+        while (lo_r < hi_r) { const int mid = (lo_r + hi_r) >> 1; if (p.dense_term[mid] < t) lo_r = mid + 1; else hi_r = mid; }
+        const bool dense = lo_r < p.n_dense && p.dense_term[lo_r] == t;
+        p.ws.tq_start[slot] = dense ? -int64_t(lo_r + 1) : s;
+        p.ws.tq_len[slot] = dense ? int32_t(p.N) : int32_t(e - s);
         p.ws.tq_mult[slot] = float(mult);
       }
       base += __popc(m);
@@ -324,6 +344,35 @@ __global__ void __launch_bounds__(256) bm25_prepare_kernel(const Bm25Params p) {
     ex = ex > 60 ? 60 : (ex < -60 ? -60 : ex);
     const float scale = ldexpf(1.0f, ex);
     __syncwarp();
+    if (p.n_dense > 0 && base > 1) {
+      // terms with a dense row go first (stable partition): every slab's first table then holds all of them
+      constexpr int R = BM25_MAXT / 32;
+      int64_t ss[R]; int32_t ll[R]; float mm[R]; int pos_d[R]; bool dd[R], vv[R];
+      int nd = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        vv[r] = i < base; ss[r] = 0; ll[r] = 0; mm[r] = 0.f;
+        if (vv[r]) { const size_t slot = size_t(q) * p.TS + i; ss[r] = p.ws.tq_start[slot]; ll[r] = p.ws.tq_len[slot]; mm[r] = p.ws.tq_mult[slot]; }
+        dd[r] = vv[r] && ss[r] < 0;
+        const uint32_t m = __ballot_sync(0xffffffffu, dd[r]);
+        pos_d[r] = nd + __popc(m & ((1u << lane) - 1));
+        nd += __popc(m);
+      }
+      __syncwarp();
+      int ns = 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const bool sp = vv[r] && !dd[r];
+        const uint32_t m = __ballot_sync(0xffffffffu, sp);
+        if (vv[r]) {
+          const size_t slot = size_t(q) * p.TS + (dd[r] ? pos_d[r] : nd + ns + __popc(m & ((1u << lane) - 1)));
+          p.ws.tq_start[slot] = ss[r]; p.ws.tq_len[slot] = ll[r]; p.ws.tq_mult[slot] = mm[r];
+        }
+        ns += __popc(m);
+      }
+      __syncwarp();
+    }
     for (int t = lane; t < base; t += 32) p.ws.tq_mult[size_t(q) * p.TS + t] *= scale;
     if (lane == 0) { p.ws.q_nt[q] = base; p.ws.q_inv_scale[q] = ldexpf(1.0f, -ex); }
   }
@@ -344,57 +393,199 @@ __device__ __forceinline__ int bm25_note_threshold(const Bm25Params& p, const Bm
   return thr_i < 1 ? 1 : thr_i;
 }
 
-// End of a slab: ranks the slab's hot docs (or the whole slab) and re-zeroes it.
-__device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, int slab0_, int thr_note) {
+// a doc whose running score reached the threshold (rare); false = the list is full, the slab will be scanned in full
+__device__ __forceinline__ bool bm25_note_hot(Bm25Shared& sh, int hb, int doc) {
+  const uint32_t at = uint32_t(atomicAdd(&sh.hot_cnt[hb], 1));
+  if (at < uint32_t(BM25_HOT)) { sh.hot[hb][at] = doc; return true; }
+  return false;
+}
+
+__device__ __forceinline__ float4 ldg_stream_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+// One pass of a slab's initialisation over one dense row: acc[d] (+)= rn(row[d] * ms).  A thread owns the int4 groups
+// tid, tid + 512, ...: plain 16-byte stores, no atomics; BM25_INIT_BATCH row loads are in flight per thread.  `lim` =
+// floats of the row from the slab's first doc on (multiple of 4).  The last pass checks the sums against the note threshold.
+constexpr int BM25_INIT_BATCH = 4;
+template <bool FIRST>
+__device__ __forceinline__ bool bm25_init_pass(Bm25Shared& sh, int4* a4, int iters, const float* row, float ms, int lim, int slab0,
+                                               int thr_i, bool last, int hb) {
+  const int tid = threadIdx.x;
+  bool noted = false;
+  for (int i0 = 0; i0 < iters; i0 += BM25_INIT_BATCH) {
+    float4 v[BM25_INIT_BATCH];
+#pragma unroll
+    for (int u = 0; u < BM25_INIT_BATCH; ++u) {
+      const int off = 4 * (tid + (i0 + u) * BM25_CONSUMERS);
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i0 + u < iters && off < lim) v[u] = ldg_stream_f32x4(row + off);
+    }
+#pragma unroll
+    for (int u = 0; u < BM25_INIT_BATCH; ++u) {
+      if (i0 + u < iters) {
+        const int g = tid + (i0 + u) * BM25_CONSUMERS;
+        int4 s = make_int4(0, 0, 0, 0);
+        if (!FIRST) s = a4[g];
+        s.x += __float2int_rn(v[u].x * ms); s.y += __float2int_rn(v[u].y * ms);
+        s.z += __float2int_rn(v[u].z * ms); s.w += __float2int_rn(v[u].w * ms);
+        a4[g] = s;
+        if (last && max(max(s.x, s.y), max(s.z, s.w)) >= thr_i) {
+          noted = true;
+          const int doc = slab0 + 4 * g;
+          if (s.x >= thr_i) bm25_note_hot(sh, hb, doc);
+          if (s.y >= thr_i) bm25_note_hot(sh, hb, doc + 1);
+          if (s.z >= thr_i) bm25_note_hot(sh, hb, doc + 2);
+          if (s.w >= thr_i) bm25_note_hot(sh, hb, doc + 3);
+        }
+      }
+    }
+  }
+  return noted;
+}
+
+// Begin of a slab: the accumulators are set to the summed contributions of the query's dense-row terms (zero without any)
+// -- this replaces both the re-zeroing of the slab and every shared-memory atomic of those terms.  `dm` = lanes of the slab's
+// first table that hold a dense run; r_lo / r_hi = the lane's run start (element of dense_rows at the slab's first doc),
+// r_mult = multiplicity x scale.  Returns whether this thread noted a hot doc.  Ends behind a barrier.
+__device__ __noinline__ bool bm25_slab_init(const Bm25Params& p, Bm25Shared& sh, int slab0, uint32_t dm, uint32_t r_lo, int r_hi,
+                                            float r_mult, int thr_i, int hb) {
+  const int tid = threadIdx.x;
+  const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
+  int4* a4 = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
+  const int iters = p.slab / BM25_SLAB_STEP;
+  bool noted = false;
+  if (dm == 0) {
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) a4[tid + i * BM25_CONSUMERS] = make_int4(0, 0, 0, 0);
+  } else {
+    const int64_t left = p.dense_stride - int64_t(slab0);
+    const int lim = left < int64_t(p.slab) ? int(left) : p.slab;
+    bool first = true;
+    while (dm) {
+      const int t = __ffs(dm) - 1; dm &= dm - 1;
+      const float* row = p.dense_rows + (int64_t(__shfl_sync(0xffffffffu, r_lo, t)) | (int64_t(__shfl_sync(0xffffffffu, r_hi, t)) << 32));
+      const float ms = __shfl_sync(0xffffffffu, r_mult, t);
+      const bool last = dm == 0;
+      noted |= first ? bm25_init_pass<true>(sh, a4, iters, row, ms, lim, slab0, thr_i, last, hb)
+                     : bm25_init_pass<false>(sh, a4, iters, row, ms, lim, slab0, thr_i, last, hb);
+      first = false;
+    }
+  }
+  cbar();                                                 // the slab is initialised before anybody adds into it
+  return noted;
+}
+
+// End of a slab: ranks the slab's hot docs (or the whole slab).  The accumulators are left as they are: the next slab's
+// initialisation overwrites them.  `noted` = this thread noted a hot doc in the slab; the verdict "somebody did" travels with
+// the barrier itself.  Usual hot case (a few docs reached the threshold): warp 0 alone reads their final scores and appends
+// them to the candidate buffer; the other warps only wait for the read-out (a flag), not for the appends -- the threshold
+// does not move until the buffer overflows.  The hot lists are double-buffered by slab parity, and the candidate count is
+// only changed by warp 0 before it arrives at the next barrier, so every thread sees the same counts behind the barrier.
+// `seq` = slabs this CTA has ended so far.
+#ifdef LRAG_BM25_TIMING
+#define BM25_PATH(x) (*path_out = (x))
+__device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, int slab0_, int thr_note, bool noted, int seq, int* path_out) {
+#else
+#define BM25_PATH(x) ((void)0)
+__device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, int slab0_, int thr_note, bool noted, int seq) {
+#endif
   const int tid = threadIdx.x;
   const NamedBarrier cbar{BM25_BAR_CONSUMERS, BM25_CONSUMERS};
   const int SLAB = p.slab, cap = p.cap;
   int* acci = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(&sh) + BM25_SH_BYTES);
   uint64_t* cand = reinterpret_cast<uint64_t*>(acci + SLAB);
   const int64_t slab0 = slab0_;
-  const float inv_scale = sh.inv_scale;
-  const int64_t range_end = sh.range_end;
-  cbar();                                                 // every add of the slab is done
-  const int nh = sh.hot_cnt;
-  if (p.nonneg && nh == 0) {
-    // nothing reached the threshold (the usual case once a few slabs have been seen): clear the slab, keep the threshold
-    float4* z4 = reinterpret_cast<float4*>(acci);
-#pragma unroll 4
-    for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
-    cbar();
+  const bool any = consumers_bar_or(noted);               // every add of the slab is done
+  // nothing reached the threshold (the usual case once a few slabs have been seen): keep the threshold
+  BM25_PATH(0);
+  if (p.nonneg && !any) return thr_note;
+  const int hb = seq & 1;
+  const int nh = sh.hot_cnt[hb];
+  const int cnt_before = sh.cand_cnt;
+  const bool listed = p.nonneg && nh <= BM25_HOT;         // the hot list holds every doc that may have reached the threshold
+  const bool fast = listed && cnt_before + nh <= cap;     // ... and the candidate buffer has room for all of them
+  BM25_PATH(fast ? 1 : 2);
+  if (fast && tid >= 32) {
+    // ---- the other warps: the hot docs' accumulators must have been read before the next slab overwrites them ----
+    if (lds_volatile(&sh.drained) != seq) {
+      const long long t0 = clock64();
+      while (lds_volatile(&sh.drained) != seq) {
+        if (clock64() - t0 > 20000000000LL) { printf("lrag: bm25 hot-list wait timed out (block %d thread %d)\n", blockIdx.x, tid); __trap(); }
+      }
+    }
     return thr_note;
   }
-  const int cnt_before = sh.cand_cnt;
-  const unsigned long long thr_key = sh.thr_key;
-  // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
-  const float thr_s = !thr_key ? -INFINITY
-                      : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
-  // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s
-  int thr_i = INT_MIN;
-  if (thr_s > -INFINITY) {
-    const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
-    thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
-    if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
-  }
-  if (p.nonneg && nh <= BM25_HOT && cnt_before + nh <= cap) {
-    if (nh > 0) {
-      // ---- the hot docs: final score -> candidate (a doc noted twice is taken once: the read clears it) ----
-      for (int i0 = 0; i0 < nh; i0 += BM25_CONSUMERS) {
-        const int i = i0 + tid;
-        bool want = false;
-        uint64_t key = 0;
-        if (i < nh) {
-          const int doc = sh.hot[i];
-          const int val = atomicExch(acci + (doc - int(slab0)), 0);
-          const float sc = float(val) * inv_scale;
-          want = val >= thr_i && sc >= thr_s && int64_t(doc) < range_end;
-          if (want) { key = make_key(sc, uint32_t(doc)); want = key > thr_key; }
+  const float inv_scale = sh.inv_scale;
+  const int64_t range_end = sh.range_end;
+  // warp 0: final score of every hot doc -> candidate (a doc noted twice is taken once: the read clears it).  With
+  // `publish`, the flag the other warps wait for is raised as soon as the last read-out has returned, before the appends.
+  auto drain = [&](unsigned long long thr_key, float thr_s, int thr_i, bool publish) {
+    for (int i0 = 0; i0 < nh; i0 += 32) {
+      const int i = i0 + tid;
+      int doc = 0, val = 0;
+      if (i < nh) { doc = sh.hot[hb][i]; val = atomicExch(acci + (doc - int(slab0)), 0); }
+      if (publish && i0 + 32 >= nh) {
+        const int dep = __reduce_or_sync(0xffffffffu, val);       // every read-out has returned
+        if (tid == 0) {
+          sh.hot_cnt[hb] = 0;
+          asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&sh.drained)), "r"(seq), "r"(dep) : "memory");
         }
-        if (i0 + (tid & ~31) < nh) cand_append(want, key, cand, cap, &sh.cand_cnt);
       }
-      cbar();                                             // hot docs are read before the slab is cleared
+      const float sc = float(val) * inv_scale;
+      bool want = i < nh && val >= thr_i && sc >= thr_s && int64_t(doc) < range_end;
+      uint64_t key = 0;
+      if (want) { key = make_key(sc, uint32_t(doc)); want = key > thr_key; }
+      cand_append(want, key, cand, cap, &sh.cand_cnt);
+    }
+  };
+  if (fast) {
+    // nonneg: thr_key is never 0 and the note threshold is the fixed-point bound of the current threshold score
+    const unsigned long long thr_key = sh.thr_key;
+    const float thr_s = (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+    drain(thr_key, thr_s, thr_note, true);
+    return thr_note;
+  }
+  if (listed) {
+    // ---- the candidate buffer is full: its exact k-th best becomes the threshold and only the k best stay (the slab is
+    //      not scanned: every doc of it that can matter is on the hot list) ----
+    BM25_PATH(3);
+    Bm25Cands cands{cand, cnt_before};
+    const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
+    uint64_t keep[BM25_KEEP];       // cap <= 2 * LRAG_MAX_K: at most BM25_KEEP old keys per thread
+#pragma unroll
+    for (int i = 0; i < BM25_KEEP; ++i) {
+      const int idx = tid + i * BM25_CONSUMERS;
+      keep[i] = idx < cnt_before ? cand[idx] : 0ull;
+    }
+    cbar();
+    if (tid == 0) { sh.cand_cnt = 0; if (pivot > sh.thr_key) sh.thr_key = pivot; }
+    cbar();
+#pragma unroll
+    for (int i = 0; i < BM25_KEEP; ++i) {
+      const bool want = keep[i] != 0ull && keep[i] >= pivot;
+      cand_append(want, keep[i], cand, cap, &sh.cand_cnt);
+    }
+    cbar();
+    if (tid < 32) {
+      const unsigned long long thr_key = sh.thr_key;
+      const float thr_s = (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+      drain(thr_key, thr_s, bm25_note_threshold(p, sh), false);
     }
   } else {
+    const unsigned long long thr_key = sh.thr_key;
+    // initial thresholds: nothing yet (-inf), or "strictly positive" when zero scores are filled in later
+    const float thr_s = !thr_key ? -INFINITY
+                        : (uint32_t(thr_key) == 0xffffffffu && key_score(thr_key) == 0.f) ? 1.4e-45f : key_score(thr_key);
+    // thr_i is a lower bound of every fixed-point value whose fp32 score reaches thr_s
+    int thr_i = INT_MIN;
+    if (thr_s > -INFINITY) {
+      const float t = thr_s / inv_scale;                     // inv_scale is a power of two: exact
+      thr_i = t >= 2147483520.f ? INT_MAX : (t <= -2147483520.f ? INT_MIN : int(floorf(t - fabsf(t) * 2.4e-7f)) - 1);
+      if (p.nonneg && thr_i < 1) thr_i = 1;                  // zero scores are never candidates then
+    }
     // ---- scan the slab for candidates ----
     const int4* a4 = reinterpret_cast<const int4*>(acci);
 #pragma unroll 2
@@ -415,6 +606,7 @@ __device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, i
     }
     cbar();
     if (sh.cand_cnt > cap) {
+      BM25_PATH(3);
       // ---- overflow: exact k-th best of (buffer U slab) becomes the new threshold ----
       Bm25Union uni{cand, cnt_before, acci, inv_scale, slab0, range_end, thr_key, SLAB};
       const unsigned long long pivot = block_select_pivot(uni, p.k, sh.sel, cbar);
@@ -441,15 +633,10 @@ __device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, i
       }
       cbar();
       if (tid == 0 && pivot > sh.thr_key) sh.thr_key = pivot;
-      cbar();
     }
   }
-  // ---- re-zero the slab for the next one ----
-  float4* z4 = reinterpret_cast<float4*>(acci);
-#pragma unroll 4
-  for (int i = 0; i < SLAB / BM25_SLAB_STEP; ++i) z4[tid + i * BM25_CONSUMERS] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tid == 0) sh.hot_cnt = 0;
-  cbar();
+  if (tid == 0) sh.hot_cnt[hb] = 0;
+  cbar();                                                 // the slab is read and the threshold set before the next slab begins
   return bm25_note_threshold(p, sh);
 }
 
@@ -491,8 +678,9 @@ __device__ __noinline__ void bm25_item_end(const Bm25Params& p, Bm25Shared& sh, 
     const int ncand = min(sh.cand_cnt, cap);
     Bm25Cands cands{cand, ncand};
     const unsigned long long pivot = block_select_pivot(cands, p.k, sh.sel, cbar);
-    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acci);     // the (zeroed) slab doubles as the sort buffer
+    uint64_t* sortbuf = reinterpret_cast<uint64_t*>(acci);     // the slab (dead between items) doubles as the sort buffer
     const int P = p.P;
+    for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;
     if (tid == 0) sh.sel.nsel = 0;
     cbar();
     for (int i = tid; i < ncand; i += BM25_CONSUMERS) {
@@ -503,8 +691,6 @@ __device__ __noinline__ void bm25_item_end(const Bm25Params& p, Bm25Shared& sh, 
     block_sort_desc(sortbuf, P, cbar);
     uint64_t* out = p.ws.out_keys + size_t(chain) * p.k;
     for (int i = tid; i < p.k; i += BM25_CONSUMERS) out[i] = sortbuf[i];
-    cbar();
-    for (int i = tid; i < P; i += BM25_CONSUMERS) sortbuf[i] = 0;   // leave the slab zeroed
     cbar();
   } else {
     const int cnt = min(sh.cand_cnt, cap);
@@ -530,14 +716,13 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
   if (tid == 0) {
     sh.cand_cnt = 0;
     sh.thr_key = 0ull;
-    sh.hot_cnt = 0;
+    sh.hot_cnt[0] = sh.hot_cnt[1] = 0;
+    sh.drained = -1;
     for (int s = 0; s < 2; ++s) { mbar_init(&sh.bfull_bar[s], 1); mbar_init(&sh.bempty_bar[s], 1); }
     fence_barrier_init();
   }
   if (tid < BM25_TABS) { sh.tab[tid].tag = 0; sh.tab[tid].arrived = BM25_WARPS; }
-  // zero the slab once; every slab end leaves it zeroed again
-  for (int i = tid; i < SLAB / 4; i += BM25_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
+  __syncthreads();                 // (the accumulators are initialised at the beginning of every slab)
   if (warp == BM25_CONSUMERS / 32 + 1) {
     // ===================== bounds warp =====================
     const int64_t item_docs = int64_t(p.item_slabs) * SLAB;
@@ -565,7 +750,8 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
         for (int t = lane; t < nt; t += 32) sh.t_cur[t] = __ldcg(p.ws.ch_cur + size_t(chain) * p.TS + t);
       } else {
         for (int t = lane; t < nt; t += 32)
-          sh.t_cur[t] = split_begin == 0 ? 0 : lower_bound_doc(p.doc_id + sh.t_start[t], 0, sh.t_len[t], split_begin);
+          sh.t_cur[t] = split_begin == 0 ? 0
+                        : (sh.t_start[t] < 0 ? int(split_begin) : lower_bound_doc(p.doc_id + sh.t_start[t], 0, sh.t_len[t], split_begin));
       }
       __syncwarp();
       int gs = nt > 0 ? BM25_BOUND_CAP / nt - 1 : BM25_MAX_GROUP;
@@ -596,7 +782,8 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
             // ids are strictly increasing inside a term: the answer is at most (target - b0) past cur
             const int64_t reach = int64_t(cur) + (target - b0);
             const int hi = int(reach < len ? reach : int64_t(len));
-            G.bound[w] = (j == 0) ? cur : lower_bound_doc(p.doc_id + sh.t_start[t], cur, hi, target);
+            G.bound[w] = (j == 0) ? cur
+                         : (sh.t_start[t] < 0 ? int(target) : lower_bound_doc(p.doc_id + sh.t_start[t], cur, hi, target));   // dense row: doc offset
           }
           __syncwarp();
           if (lane < ns) {
@@ -657,10 +844,15 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
           Bm25Tab* tb = acquire();
           const int t = t0 + lane;
           int64_t first = 0; int cnt = 0; float mult = 0.f;
+          bool dense = false;
           if (t < nt) {
             const int lo = G.bound[t * (ns + 1) + j];
             cnt = G.bound[t * (ns + 1) + j + 1] - lo;
-            first = G.t_start[t] + lo;
+            const int64_t ts = G.t_start[t];
+            dense = ts < 0;
+            // dense row: no postings to walk; `first` = element of dense_rows at the slab's first doc (the slab initialisation reads it)
+            if (dense) cnt = 0;
+            first = dense ? (-ts - 1) * p.dense_stride + sl0 : ts + lo;
             mult = G.t_mult[t];
           }
           // chunks of a run: BM25_SEG postings each, counted from the 32-posting (128-byte) boundary at or below its first
@@ -669,10 +861,11 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
           tb->first_lo[lane] = int(uint32_t(first)); tb->first_hi[lane] = int(uint32_t(first >> 32));
-          tb->cnt[lane] = cnt; tb->cpre[lane] = incl - nch; tb->mult[lane] = mult;
+          tb->cnt[lane] = cnt | (dense ? BM25_DENSE_FLAG : 0); tb->cpre[lane] = incl - nch; tb->mult[lane] = mult;
           const int total = __shfl_sync(0xffffffffu, incl, 31);
           const bool last_tab = t0 + 32 >= nt;
-          publish(tb, last_tab ? BM25_F_SLAB_END : 0, sl0, min(32, max(nt - t0, 0)), total, chain, step, 0.f);
+          publish(tb, (last_tab ? BM25_F_SLAB_END : 0) | (t0 == 0 ? BM25_F_SLAB_BEGIN : 0), sl0, min(32, max(nt - t0, 0)), total, chain,
+                  step, 0.f);
         }
       }
       if (G.last) publish(acquire(), BM25_F_ITEM_END | (G.final_step ? BM25_F_FINAL : 0), 0, 0, 0, chain, step, 0.f);
@@ -684,7 +877,8 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
     // Scores are accumulated in fixed point (int32, per-query power-of-two scale) with shared-memory
     // integer atomics: adds commute exactly, so the pieces of a slab need no ordering between them,
     // results do not depend on which warp ran first, and one ATOMS replaces a load / add / store.
-    const uint32_t hot_u32 = smem_u32(sh.hot), hotc_u32 = smem_u32(&sh.hot_cnt);
+    const uint32_t hot_u32 = smem_u32(sh.hot), hotc_u32 = smem_u32(sh.hot_cnt);
+    int seq = 0;              // slabs ended so far; its parity selects the hot list
     const uint32_t acc_u32 = smem_u32(acc);
     int thr_i = INT_MAX;      // an add whose doc reaches this fixed-point score notes the doc
     int thr_slab = INT_MAX;   // thr_i at the start of the slab (a thread that saw the hot list overflow stops noting)
@@ -694,17 +888,26 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
       const int vi = __float2int_rn(imp * ms);
       return atoms_add_s32(accb + 4u * uint32_t(doc), vi) + vi;
     };
+    bool noted = false;       // this thread noted a hot doc in the current slab
     // note a doc whose running score reached the threshold (rare)
     auto note_hot = [&](int doc) {
       uint32_t at;
-      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(hotc_u32) : "memory");
-      if (at < uint32_t(BM25_HOT)) asm volatile("st.shared.s32 [%0], %1;" ::"r"(hot_u32 + 4u * at), "r"(doc) : "memory");
+      const uint32_t hb = uint32_t(seq & 1);
+      asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(hotc_u32 + 4u * hb) : "memory");
+      noted = true;
+      if (at < uint32_t(BM25_HOT)) asm volatile("st.shared.s32 [%0], %1;" ::"r"(hot_u32 + 4u * (hb * BM25_HOT + at)), "r"(doc) : "memory");
       else thr_i = INT_MAX;                                    // overflow: the slab will be scanned in full
     };
 
+#ifdef LRAG_BM25_TIMING
+    long long tacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     for (int rd = 0;; ++rd) {
       // ---- next slab table ----
       Bm25Tab* tb = &sh.tab[rd & (BM25_TABS - 1)];
+#ifdef LRAG_BM25_TIMING
+      const long long tw0 = clock64();
+#endif
       {
         const int want = rd / BM25_TABS + 1;
         long long t0 = 0;
@@ -717,6 +920,9 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
           }
         }
       }
+#ifdef LRAG_BM25_TIMING
+      tacc[0] += clock64() - tw0; tacc[5] += 1;
+#endif
       asm volatile("" ::: "memory");            // shared-memory loads of one thread are performed in order
       int4 h0, h1;
       asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(h0.x), "=r"(h0.y), "=r"(h0.z), "=r"(h0.w)
@@ -733,15 +939,26 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
       }
       __syncwarp();
       if (lane == 0) atomicAdd(&tb->arrived, 1);           // the table is in registers: its slot may be rewritten
-      if (flags & BM25_F_ITEM_BEGIN) thr_slab = thr_i = bm25_item_begin(p, sh, h1.x, h1.y, __int_as_float(h1.z));
+      if (flags & BM25_F_ITEM_BEGIN) BM25_T(4, thr_slab = thr_i = bm25_item_begin(p, sh, h1.x, h1.y, __int_as_float(h1.z)));
+      // ---- first table of a slab: initialise the accumulators from the dense-row terms (or zero them) ----
+      if (flags & BM25_F_SLAB_BEGIN) {
+        const uint32_t dm = __ballot_sync(0xffffffffu, lane < nruns && (r_cnt & BM25_DENSE_FLAG) != 0);
+        BM25_T(1, noted = bm25_slab_init(p, sh, slab0, dm, r_lo, r_hi, r_mult, thr_i, seq & 1));
+      }
       // ---- this warp's chunks of the slab: c = warp, warp + 16, ...; 8 coalesced (doc, impact) loads per lane, then the adds ----
       const uint32_t accb = acc_u32 - 4u * uint32_t(slab0);        // accb + 4 * doc == &acc[doc - slab0]
+#ifdef LRAG_BM25_TIMING
+      const long long tc0 = clock64();
+#endif
       for (int c = warp; c < nchunks; c += BM25_WARPS) {
+#ifdef LRAG_BM25_TIMING
+        tacc[6] += 1;
+#endif
         // the run that holds chunk c: the last one whose chunk prefix is <= c
         const int t = __popc(__ballot_sync(0xffffffffu, r_cpre <= c)) - 1;
         const uint32_t f_lo = __shfl_sync(0xffffffffu, r_lo, t);
         const int f_hi = __shfl_sync(0xffffffffu, r_hi, t);
-        const int cnt = __shfl_sync(0xffffffffu, r_cnt, t);
+        const int cnt = __shfl_sync(0xffffffffu, r_cnt, t) & (BM25_DENSE_FLAG - 1);
         const int j = c - __shfl_sync(0xffffffffu, r_cpre, t);
         const float ms = __shfl_sync(0xffffffffu, r_mult, t);      // term multiplicity x scale
         const int64_t first = int64_t(f_lo) | (int64_t(f_hi) << 32);
@@ -776,12 +993,37 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
             if (d[u] >= 0 && add_posting(accb, d[u], v[u], ms) >= thr_i) note_hot(d[u]);
         }
       }
+#ifdef LRAG_BM25_TIMING
+      const long long tc1 = clock64();
+      tacc[2] += tc1 - tc0;
+      if (flags & BM25_F_SLAB_END) tacc[7] += 1;
+#endif
       // ---- markers: every consumer warp sees the same ones ----
-      if (flags & BM25_F_SLAB_END) thr_slab = bm25_slab_end(p, sh, slab0, thr_slab);
-      if (flags & BM25_F_ITEM_END) bm25_item_end(p, sh, h1.x, h1.y, flags & BM25_F_FINAL);
+      if (flags & BM25_F_SLAB_END) {
+#ifdef LRAG_BM25_TIMING
+        int path = 0;
+        const long long te0 = clock64();
+        thr_slab = bm25_slab_end(p, sh, slab0, thr_slab, noted, seq, &path); noted = false;
+        const long long te1 = clock64();
+        tacc[3] += te1 - te0; tacc[8 + path] += te1 - te0; tacc[12 + path] += 1;
+#else
+        thr_slab = bm25_slab_end(p, sh, slab0, thr_slab, noted, seq); noted = false;
+#endif
+#ifdef LRAG_BM25_TIMING
+        if (blockIdx.x == 0 && seq < 1024 && lane == 0) {
+          long long* tr = g_bm25_trace + (size_t(seq) * 16 + warp) * 4;
+          tr[0] = tc0; tr[1] = tc1; tr[2] = (nchunks > warp) ? (nchunks - warp + BM25_WARPS - 1) / BM25_WARPS : 0; tr[3] = clock64();
+        }
+#endif
+        ++seq;
+      }
+      if (flags & BM25_F_ITEM_END) BM25_T(4, bm25_item_end(p, sh, h1.x, h1.y, flags & BM25_F_FINAL));
       if (flags & BM25_F_END) break;
       thr_i = thr_slab;
     }
+#ifdef LRAG_BM25_TIMING
+    if (lane == 0) for (int i = 0; i < 16; ++i) atomicAdd(&g_bm25_t[i], (unsigned long long)tacc[i]);
+#endif
   }
 }
 
@@ -908,6 +1150,20 @@ static Bm25Plan bm25_plan(int64_t N, int nq, int k, int64_t max_query_terms, int
 
 using namespace lrag;
 
+#ifdef LRAG_BM25_TIMING
+extern "C" int lrag_bm25_debug_timing(unsigned long long* out, int reset) {
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (reset) return cudaMemcpyToSymbol(g_bm25_t, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(out, g_bm25_t, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+#ifdef LRAG_BM25_TIMING
+extern "C" int lrag_bm25_debug_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, g_bm25_trace, sizeof(long long) * 1024 * 16 * 4) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 extern "C" int lrag_bm25_set_item_slabs(int slabs) {
   LRAG_REQUIRE(slabs >= 0 && slabs <= 4096, "bm25_set_item_slabs: %d out of range (0 = default, max 4096)", slabs);
   g_item_slabs = slabs;
@@ -923,7 +1179,20 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
                               const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                               int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
                               int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
+  return lrag_bm25_topk_dense(indptr, doc_id, impact, V, nnz, nullptr, nullptr, 0, 0, q_indptr, q_term, nq, max_query_terms, N, k,
+                              id_base, nonneg, impact_bound, out_score, out_id, ws, ws_bytes, stream_);
+}
+
+extern "C" int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
+                                    const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
+                                    const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                                    int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
+                                    int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LRAG_REQUIRE(n_dense >= 0 && n_dense <= 32 && (n_dense == 0 || (dense_term && dense_rows && dense_stride >= N && dense_stride % 32 == 0 &&
+                                                (reinterpret_cast<uintptr_t>(dense_rows) & 127) == 0)),
+               "bm25_topk: dense rows (at most 32) need sorted term ids, 128-byte aligned rows and a row stride >= N that is a multiple of 32 "
+               "(n_dense=%d stride=%lld)", n_dense, (long long)dense_stride);
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && k > 0 && k <= LRAG_MAX_K, "bm25_topk: need nq > 0 and 1 <= k <= %d (nq=%d k=%d)", LRAG_MAX_K, nq, k);
   LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31) - BM25_SLAB_MAX, "bm25_topk: N=%lld out of range for one shard", (long long)N);
@@ -942,6 +1211,7 @@ extern "C" int lrag_bm25_topk(const int64_t* indptr, const int32_t* doc_id, cons
   uint8_t* w = static_cast<uint8_t*>(ws);
   Bm25Params p;
   p.indptr = indptr; p.doc_id = doc_id; p.impact = impact; p.V = V; p.nnz = nnz; p.q_indptr = q_indptr; p.q_term = q_term;
+  p.dense_term = dense_term; p.dense_rows = dense_rows; p.n_dense = n_dense; p.dense_stride = dense_stride;
   p.N = N; p.dps = pl.dps; p.total_items = pl.total_items; p.nq = nq; p.k = k; p.nonneg = nonneg ? 1 : 0;
   p.S = pl.S; p.cap = pl.cap; p.P = pl.P; p.TS = pl.TS; p.item_slabs = pl.item_slabs; p.steps = pl.steps; p.nc = pl.nc; p.slab = pl.slab;
   p.ws.counter = reinterpret_cast<unsigned long long*>(w + pl.off[0]);

@@ -299,6 +299,38 @@ def test_bm25_synthetic_multi_slab_and_split(eng):
                           TAU_FP32, what="bm25-shard")
 
 
+def test_bm25_dense_rows_change_nothing_but_the_speed(eng):
+    """Terms that occur in most documents are walked through a dense impact row instead of their posting list
+    (lrag_bm25_topk_dense): same fixed-point sums, so bit-identical scores and ids -- at several slab / item / split shapes,
+    with a range end inside a chunk, and with a repeated dense term in a query."""
+    from legal_rag_b200 import synth
+    for N, V, nq, k, mean_len in ((70_001, 300, 300, 100, 40.0), (5_000, 50, 7, 20, 30.0), (300_000, 2_000, 40, 50, 24.0)):
+        index, st = synth.bm25_synthetic_index(N, V, 77, "cuda", mean_len=mean_len)
+        q_indptr, q_term, mx = synth.bm25_synthetic_queries(nq, V, 78, "cuda")
+        q_term[:2] = 0                                           # the head term twice in the first query
+        for item_slabs in (0, 1):
+            eng.bm25_set_item_slabs(item_slabs)
+            try:
+                index._dense_built, index.dense_term, index.dense_rows = True, None, None      # posting lists only
+                s0, i0 = eng.bm25_topk(index, q_indptr, q_term, mx, k)
+                n_rows = index.build_dense_rows()
+                assert n_rows >= 1 and index.dense_rows.shape[1] % 32 == 0
+                s1, i1 = eng.bm25_topk(index, q_indptr, q_term, mx, k)
+            finally:
+                eng.bm25_set_item_slabs(0)
+            assert torch.equal(i0, i1) and torch.equal(s0, s1), f"dense rows changed the result (N={N}, item_slabs={item_slabs})"
+    # impacts that may be negative: every slab is ranked in full, zero-score docs included; rows and posting lists still agree
+    index, st = synth.bm25_synthetic_index(30_000, 200, 79, "cuda", mean_len=30.0)
+    index.impact[::7] *= -1.0
+    index.nonneg = False
+    q_indptr, q_term, mx = synth.bm25_synthetic_queries(25, 200, 80, "cuda")
+    index._dense_built, index.dense_term, index.dense_rows = True, None, None
+    s0, i0 = eng.bm25_topk(index, q_indptr, q_term, mx, 64)
+    assert index.build_dense_rows(min_density=0.3) >= 1
+    s1, i1 = eng.bm25_topk(index, q_indptr, q_term, mx, 64)
+    assert torch.equal(i0, i1) and torch.equal(s0, s1), "dense rows changed the result (negative impacts)"
+
+
 def test_bm25_negative_average_idf_ranks_every_document(eng):
     """3-doc corpus whose epsilon-floored idf is negative (tests/test_oracle.py's hand-computed case):
     zero-score documents then outrank matched ones and no slab may be skipped."""
