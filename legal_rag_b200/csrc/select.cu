@@ -409,6 +409,183 @@ topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id
                     out_id + size_t(q) * k, static_cast<uint64_t*>(nullptr), col_id ? col_id + size_t(q) * N : nullptr);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Many medium rows (a few thousand to ~10^5 scores each, e.g. 4096 x 20 000): one WARP per row.  A row that is a handful of
+// trips long cannot amortise a CTA's per-row costs (threshold bootstrap, final select, merge launch: ~14 barriers each), and
+// one CTA per row re-reads the row once per radix pass.  Here a warp streams its row once -- sixteen scores per lane per trip
+// in four 16-byte loads -- behind a per-lane threshold filter, keeps candidates in its own slice of shared memory, cuts them
+// back to the k best with a warp-level radix select whenever the slice fills (which also raises the threshold), and finally
+// sorts its k keys and writes the row's result itself.  No CTA-wide barrier anywhere, no second kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int WROW_WARPS = 8;                            // rows (warps) per CTA
+constexpr int WROW_PER_LANE = 16;
+constexpr int WROW_TRIP = 32 * WROW_PER_LANE;            // 512 scores per warp trip
+constexpr int WROW_MAX_K = 256;
+
+// pivot such that exactly k of keys[0, n) are >= pivot (n >= k); warp-level counterpart of block_select_pivot
+__device__ __forceinline__ unsigned long long warp_select_pivot(const uint64_t* keys, int n, int k, int* hist) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long prefix = 0, mask = 0;
+  int rem = k;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint64_t key = keys[i];
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    }
+    __syncwarp();
+    int c[8], local = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; local += c[j]; }
+    int incl = local;                                    // keys in this lane's bins and all higher bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += v;
+    }
+    const int above = incl - local;
+    const bool own = above < rem && above + local >= rem;        // exactly one lane: n >= k keys match the prefix
+    int bin = 0, nrem = 0;
+    if (own) {
+      int cum = above;
+#pragma unroll
+      for (int j = 7; j >= 0; --j) {
+        if (cum < rem && cum + c[j] >= rem) { bin = lane * 8 + j; nrem = (cum + c[j] == rem) ? 0 : rem - cum; }
+        cum += c[j];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, own)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    rem = __shfl_sync(0xffffffffu, nrem, src);
+    prefix |= (unsigned long long)bin << shift;
+    mask |= 0xffull << shift;
+    __syncwarp();
+    if (rem == 0) break;                                 // the whole bin is wanted: every key >= prefix is a winner
+  }
+  return prefix;
+}
+
+// keeps the keys >= pivot of keys[0, n) (in place, order preserved); returns how many
+__device__ __forceinline__ int warp_keep_ge(uint64_t* keys, int n, unsigned long long pivot) {
+  const int lane = threadIdx.x & 31;
+  int wr = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const uint64_t key = i < n ? keys[i] : 0ull;
+    const bool keep = i < n && key >= pivot;
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();                                        // the chunk is in registers before anything lands in it
+    if (keep) keys[wr + __popc(m & ((1u << lane) - 1))] = key;
+    wr += __popc(m);
+  }
+  __syncwarp();
+  return wr;
+}
+
+__global__ void __launch_bounds__(WROW_WARPS * 32)
+topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, int k, int P, int cap, int64_t id_base,
+                      float* __restrict__ out_score, int64_t* __restrict__ out_id) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * WROW_WARPS + warp;
+  if (q >= nq) return;                                   // warps are independent: no CTA barrier below
+  const size_t per_warp = size_t(cap + WROW_TRIP) * 8 + 256 * 4 + 16;
+  uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw + warp * per_warp);          // [cap + one trip]
+  int* hist = reinterpret_cast<int*>(keys + cap + WROW_TRIP);                      // [256]
+  int* cnt = hist + 256;
+  const float* row = S + size_t(q) * ld;
+  if (lane == 0) *cnt = 0;
+  __syncwarp();
+  unsigned long long thr_key = 0ull;
+  float thr_s = -INFINITY;
+  const float qnan = __int_as_float(0x7fc00000);         // past the row's end: NaN never reaches a threshold
+  const uint32_t cnt_s = smem_u32(cnt);
+  for (int base = 0; base < N; base += WROW_TRIP) {
+    float v[WROW_PER_LANE];
+    if (base + WROW_TRIP <= N) {
+#pragma unroll
+      for (int g = 0; g < WROW_PER_LANE / 4; ++g) {
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(row + base + (g * 32 + lane) * 4));
+        v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < WROW_PER_LANE / 4; ++g) {
+        const int e = base + (g * 32 + lane) * 4;
+        float4 x = make_float4(qnan, qnan, qnan, qnan);
+        if (e + 3 < N) x = __ldcs(reinterpret_cast<const float4*>(row + e));
+        else if (e < N) {
+          x.x = __ldg(row + e);
+          if (e + 1 < N) x.y = __ldg(row + e + 1);
+          if (e + 2 < N) x.z = __ldg(row + e + 2);
+        }
+        v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+      }
+    }
+    float vmax = -INFINITY;                              // fmaxf skips NaN: a lane with no score inside the row stays at -inf
+#pragma unroll
+    for (int i = 0; i < WROW_PER_LANE; ++i) vmax = fmaxf(vmax, v[i]);
+    if (vmax >= thr_s) {
+#pragma unroll
+      for (int i = 0; i < WROW_PER_LANE; ++i) {
+        if (v[i] >= thr_s) {
+          const uint64_t key = make_key(v[i], uint32_t(base + ((i / 4) * 32 + lane) * 4 + (i & 3)));
+          if (key > thr_key) {
+            uint32_t at;
+            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cnt_s) : "memory");
+            keys[at] = key;                              // never past cap + one trip: the slice is cut back below
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int n = *reinterpret_cast<volatile int*>(cnt);
+    if (n > cap) {
+      // ---- the slice is full: keep the k best, their k-th is the new threshold ----
+      const unsigned long long pivot = warp_select_pivot(keys, n, k, hist);
+      const int m = warp_keep_ge(keys, n, pivot);
+      if (lane == 0) *cnt = m;
+      if (pivot > thr_key) { thr_key = pivot; const float ps = key_score(pivot); thr_s = ps == ps ? ps : -INFINITY; }
+      __syncwarp();
+    }
+  }
+  // ---- the row's k best, sorted, straight to the output ----
+  int n = *reinterpret_cast<volatile int*>(cnt);
+  if (n > k) { const unsigned long long pivot = warp_select_pivot(keys, n, k, hist); n = warp_keep_ge(keys, n, pivot); }
+  for (int i = n + lane; i < P; i += 32) keys[i] = 0ull;
+  __syncwarp();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = lane; i < P / 2; i += 32) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const uint64_t a = keys[lo], b = keys[hi];
+        if (desc ? (a < b) : (a > b)) { keys[lo] = b; keys[hi] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  float* os = out_score + size_t(q) * k;
+  int64_t* oi = out_id + size_t(q) * k;
+  for (int r = lane; r < k; r += 32) {
+    const uint64_t key = r < n ? keys[r] : 0ull;
+    os[r] = key ? key_score(key) : LRAG_PAD_SCORE;
+    oi[r] = key ? id_base + int64_t(key_id(key)) : int64_t(-1);
+  }
+}
+
+static int wrow_cap(int k) { return std::max(256, 2 * next_pow2(k)); }
+static size_t wrow_smem_bytes(int k) { return size_t(WROW_WARPS) * (size_t(wrow_cap(k) + WROW_TRIP) * 8 + 256 * 4 + 16); }
+// one warp per row pays off when there are enough rows to fill the machine with warps and a row is neither tiny nor long
+// enough for the balanced runs of the streaming kernel
+static bool wrow_applies(int nq, int64_t N, int k, bool aligned, bool has_col_id) {
+  return aligned && !has_col_id && k <= WROW_MAX_K && N >= 2048 && N < 32 * STREAM_TRIP && nq >= 64;
+}
+
 // Slice length of the fixed-slice path: 2^18 scores when that already gives every SM several CTAs, shorter (down to 2^15, a
 // multiple of the trip) when there are few rows.
 static int64_t select_slice_len(int nq, int64_t N) {
@@ -467,6 +644,19 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
   uint64_t* keys = static_cast<uint64_t*>(ws);
   StreamPlan plan{};
   const bool aligned = (reinterpret_cast<uintptr_t>(S) & 15) == 0 && ld % 4 == 0;      // bulk copies need 16-byte aligned rows
+  if (wrow_applies(nq, N, k, aligned, col_id != nullptr)) {
+    static bool wrow_attr[LRAG_MAX_DEVICES] = {};
+    if (!wrow_attr[dev]) {
+      LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_warp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wrow_smem_bytes(WROW_MAX_K))));
+      wrow_attr[dev] = true;
+    }
+    prof_begin(stream, PROF_SELECT);
+    topk_warp_rows_kernel<<<(nq + WROW_WARPS - 1) / WROW_WARPS, WROW_WARPS * 32, wrow_smem_bytes(k), stream>>>(
+        S, ld, nq, int(N), k, P, wrow_cap(k), id_base, out_score, out_id);
+    prof_end(stream);
+    LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
+    return LRAG_OK;
+  }
   if (aligned && ws && stream_plan(nq, N, k, plan) && ws_bytes >= size_t(nq) * size_t(plan.spr) * size_t(k) * 8) {
     prof_begin(stream, PROF_SELECT);
     topk_stream_kernel<<<plan.grid, STREAM_THREADS, stream_smem_bytes(k, plan.trig), stream>>>(S, ld, N, k, col_id, plan, keys);

@@ -55,6 +55,25 @@ def test_topk_select_matches_oracle(eng):
         np.testing.assert_array_equal(s.cpu().numpy(), D)
 
 
+def test_topk_select_one_warp_per_row(eng):
+    """Many medium rows take the warp-per-row kernel (aligned rows, no column ids, k <= 256, 2048 <= N < 131072, >= 64 rows):
+    ragged row ends, a row stride longer than the row, runs of -inf longer than a trip, rows with fewer finite scores than
+    k, ascending rows (every trip raises the threshold), exact ties, k = 1 and k = 256."""
+    rng = np.random.default_rng(21)
+    W = rng.standard_normal((200, 140_000)).astype(np.float32)
+    W[:, ::5] = W[:, :1]
+    W[1, 1000:60_000] = -np.inf
+    W[2, :] = np.sort(W[2, :])
+    W[3, 30:] = -np.inf
+    W[4, :] = 0.5
+    Wd = torch.from_numpy(W).cuda()
+    for c0, N, k in [(0, 20_000, 100), (0, 2048, 256), (4, 131_071, 100), (8, 131_070, 1), (0, 5_001, 37), (12, 65_537, 256), (0, 70_000, 200)]:
+        s, i = eng.topk_select(Wd[:, c0:c0 + N], k, id_base=7)
+        D, I = odense.topk_rows(W[:, c0:c0 + N], k, id_base=7)
+        np.testing.assert_array_equal(i.cpu().numpy(), I, err_msg=f"c0={c0} N={N} k={k}")
+        np.testing.assert_array_equal(s.cpu().numpy(), D, err_msg=f"c0={c0} N={N} k={k}")
+
+
 def test_topk_select_column_window_of_a_wider_matrix(eng):
     """Row stride != row length: 16-byte aligned rows whose length is not a multiple of four scores (the ragged end of the
     streamed path), a window starting at an unaligned column (plain-load path), short last slices, runs of -inf."""
