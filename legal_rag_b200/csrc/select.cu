@@ -417,7 +417,7 @@ topk_merge_keys_kernel(const uint64_t* keys, int slots, int k, int P, int64_t id
 // back to the k best with a warp-level radix select whenever the slice fills (which also raises the threshold), and finally
 // sorts its k keys and writes the row's result itself.  No CTA-wide barrier anywhere, no second kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int WROW_WARPS = 8;                            // rows (warps) per CTA
+constexpr int WROW_MAX_WARPS = 16;                       // rows (warps) per CTA: 4 ... 16, chosen per launch so that the grid is whole waves
 constexpr int WROW_PER_LANE = 16;
 constexpr int WROW_TRIP = 32 * WROW_PER_LANE;            // 512 scores per warp trip
 constexpr int WROW_MAX_K = 256;
@@ -485,12 +485,12 @@ __device__ __forceinline__ int warp_keep_ge(uint64_t* keys, int n, unsigned long
   return wr;
 }
 
-__global__ void __launch_bounds__(WROW_WARPS * 32)
+__global__ void __launch_bounds__(WROW_MAX_WARPS * 32)
 topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, int k, int P, int cap, int64_t id_base,
                       float* __restrict__ out_score, int64_t* __restrict__ out_id) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * WROW_WARPS + warp;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
   if (q >= nq) return;                                   // warps are independent: no CTA barrier below
   const size_t per_warp = size_t(cap + WROW_TRIP) * 8 + 256 * 4 + 16;
   uint64_t* keys = reinterpret_cast<uint64_t*>(sm_raw + warp * per_warp);          // [cap + one trip]
@@ -503,8 +503,8 @@ topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, in
   float thr_s = -INFINITY;
   const float qnan = __int_as_float(0x7fc00000);         // past the row's end: NaN never reaches a threshold
   const uint32_t cnt_s = smem_u32(cnt);
-  for (int base = 0; base < N; base += WROW_TRIP) {
-    float v[WROW_PER_LANE];
+  // one trip of the row into registers (scores past the row's end are NaN)
+  auto load_trip = [&](int base, float (&v)[WROW_PER_LANE]) {
     if (base + WROW_TRIP <= N) {
 #pragma unroll
       for (int g = 0; g < WROW_PER_LANE / 4; ++g) {
@@ -525,20 +525,38 @@ topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, in
         v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
       }
     }
-    float vmax = -INFINITY;                              // fmaxf skips NaN: a lane with no score inside the row stays at -inf
+  };
+  // one trip: filter the lane's sixteen scores, append the hits, cut the slice back when it is full
+  auto step = [&](const float (&v)[WROW_PER_LANE], int base) {
+    // which of the lane's sixteen scores reach the threshold (NaN compares false)
+    uint32_t hm = 0;
 #pragma unroll
-    for (int i = 0; i < WROW_PER_LANE; ++i) vmax = fmaxf(vmax, v[i]);
-    if (vmax >= thr_s) {
+    for (int i = 0; i < WROW_PER_LANE; ++i) hm |= (v[i] >= thr_s ? 1u : 0u) << i;
+    if (thr_s == -INFINITY && __all_sync(0xffffffffu, hm == 0xffffu)) {
+      // no threshold yet and a whole trip inside the row: every score is a candidate, no need to count them one by one
+      const int n0 = *reinterpret_cast<volatile int*>(cnt);
 #pragma unroll
-      for (int i = 0; i < WROW_PER_LANE; ++i) {
-        if (v[i] >= thr_s) {
-          const uint64_t key = make_key(v[i], uint32_t(base + ((i / 4) * 32 + lane) * 4 + (i & 3)));
-          if (key > thr_key) {
-            uint32_t at;
-            asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cnt_s) : "memory");
-            keys[at] = key;                              // never past cap + one trip: the slice is cut back below
-          }
-        }
+      for (int i = 0; i < WROW_PER_LANE; ++i)
+        keys[n0 + i * 32 + lane] = make_key(v[i], uint32_t(base + ((i >> 2) * 32 + lane) * 4 + (i & 3)));
+      __syncwarp();
+      if (lane == 0) *cnt = n0 + WROW_TRIP;
+      hm = 0;
+    }
+    // the warp runs this loop as often as its busiest lane has hits -- once, as a rule -- instead of once per slot
+    while (hm) {
+      const int i = __ffs(hm) - 1;
+      hm &= hm - 1;
+      // v[i] by a select tree (a register array cannot be indexed dynamically)
+      const float a0 = (i & 1) ? v[1] : v[0], a1 = (i & 1) ? v[3] : v[2], a2 = (i & 1) ? v[5] : v[4], a3 = (i & 1) ? v[7] : v[6];
+      const float a4 = (i & 1) ? v[9] : v[8], a5 = (i & 1) ? v[11] : v[10], a6 = (i & 1) ? v[13] : v[12], a7 = (i & 1) ? v[15] : v[14];
+      const float b0 = (i & 2) ? a1 : a0, b1 = (i & 2) ? a3 : a2, b2 = (i & 2) ? a5 : a4, b3 = (i & 2) ? a7 : a6;
+      const float c0 = (i & 4) ? b1 : b0, c1 = (i & 4) ? b3 : b2;
+      const float x = (i & 8) ? c1 : c0;
+      const uint64_t key = make_key(x, uint32_t(base + ((i >> 2) * 32 + lane) * 4 + (i & 3)));
+      if (key > thr_key) {
+        uint32_t at;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(at) : "r"(cnt_s) : "memory");
+        keys[at] = key;                                  // never past cap + one trip: the slice is cut back below
       }
     }
     __syncwarp();
@@ -551,6 +569,17 @@ topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, in
       if (pivot > thr_key) { thr_key = pivot; const float ps = key_score(pivot); thr_s = ps == ps ? ps : -INFINITY; }
       __syncwarp();
     }
+  };
+  // the next two trips (4 KB per warp) are in flight while one is filtered; the buffers rotate by register moves (unrolling
+  // the rotation away costs 40 more registers and a third of the resident warps)
+  float v[WROW_PER_LANE], vn[WROW_PER_LANE], vnn[WROW_PER_LANE];
+  load_trip(0, v);
+  if (WROW_TRIP < N) load_trip(WROW_TRIP, vn);
+  for (int base = 0; base < N; base += WROW_TRIP) {
+    if (base + 2 * WROW_TRIP < N) load_trip(base + 2 * WROW_TRIP, vnn);
+    step(v, base);
+#pragma unroll
+    for (int i = 0; i < WROW_PER_LANE; ++i) { v[i] = vn[i]; vn[i] = vnn[i]; }
   }
   // ---- the row's k best, sorted, straight to the output ----
   int n = *reinterpret_cast<volatile int*>(cnt);
@@ -579,7 +608,21 @@ topk_warp_rows_kernel(const float* __restrict__ S, int64_t ld, int nq, int N, in
 }
 
 static int wrow_cap(int k) { return std::max(256, 2 * next_pow2(k)); }
-static size_t wrow_smem_bytes(int k) { return size_t(WROW_WARPS) * (size_t(wrow_cap(k) + WROW_TRIP) * 8 + 256 * 4 + 16); }
+static size_t wrow_smem_bytes(int k, int warps) { return size_t(warps) * (size_t(wrow_cap(k) + WROW_TRIP) * 8 + 256 * 4 + 16); }
+// Rows (warps) per CTA: the choice that wastes the fewest warp slots over the waves the grid needs.  All rows of a call
+// cost about the same, so a grid of 1.15 waves takes as long as one of 2; 4096 rows are one wave of 293 CTAs of 14 warps.
+static int wrow_pick_warps(int nq, int k) {
+  const int sms = sm_count();
+  int best = 8; double best_eff = -1.0;
+  for (int w = 4; w <= WROW_MAX_WARPS; ++w) {
+    const int per_sm = int(std::min<size_t>(std::min<size_t>((227 * 1024) / (wrow_smem_bytes(k, w) + 1024), size_t(64 / w)), 32));
+    if (per_sm < 1) continue;
+    const int64_t slots = int64_t(sms) * per_sm, grid = (nq + w - 1) / w, waves = (grid + slots - 1) / slots;
+    const double eff = double(nq) / double(waves * slots * w) * (per_sm * w >= 24 ? 1.0 : double(per_sm * w) / 24.0);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = w; }
+  }
+  return best;
+}
 // one warp per row pays off when there are enough rows to fill the machine with warps and a row is neither tiny nor long
 // enough for the balanced runs of the streaming kernel
 static bool wrow_applies(int nq, int64_t N, int k, bool aligned, bool has_col_id) {
@@ -647,11 +690,12 @@ int launch_topk_select(const float* S, int64_t ld, int nq, int64_t N, int k, int
   if (wrow_applies(nq, N, k, aligned, col_id != nullptr)) {
     static bool wrow_attr[LRAG_MAX_DEVICES] = {};
     if (!wrow_attr[dev]) {
-      LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_warp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wrow_smem_bytes(WROW_MAX_K))));
+      LRAG_CHECK_CUDA(cudaFuncSetAttribute(topk_warp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(wrow_smem_bytes(WROW_MAX_K, WROW_MAX_WARPS))));
       wrow_attr[dev] = true;
     }
     prof_begin(stream, PROF_SELECT);
-    topk_warp_rows_kernel<<<(nq + WROW_WARPS - 1) / WROW_WARPS, WROW_WARPS * 32, wrow_smem_bytes(k), stream>>>(
+    const int wr_warps = wrow_pick_warps(nq, k);
+    topk_warp_rows_kernel<<<(nq + wr_warps - 1) / wr_warps, wr_warps * 32, wrow_smem_bytes(k, wr_warps), stream>>>(
         S, ld, nq, int(N), k, P, wrow_cap(k), id_base, out_score, out_id);
     prof_end(stream);
     LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();
