@@ -91,7 +91,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -101,11 +101,17 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sm_mhz_min": min(sm) if sm else None,
+                "sm_mhz_max_seen": max(sm) if sm else None, "power_w": statistics.median(pw) if pw else None,
+                "power_w_max": max(pw) if pw else None}
 
 
 # =================================================================================================
@@ -351,6 +357,8 @@ class HybridWorkload:
         self.N, self.d, self.V = n_docs or args.n_docs or 12_500_000, args.dim or 768, args.vocab or 500_000
         self.nq, self.k, self.kc = args.nq or 4096, args.k, (getattr(args, "kc", 0) or args.k)
         self.colbert_mode = getattr(args, "colbert_mode", "rerank")
+        self.dense_sms_arg = str(getattr(args, "dense_sms", "auto"))
+        self.partition, self.alone_ms = None, {}
         # rerank: configs[4]'s 1M-doc token store (ids aliased onto it); scan: one token row per document of the shard
         self.Nd_tok, self.Ld, self.Lq = (max(1, self.N // 100), 128, 32) if self.colbert_mode == "rerank" else (self.N, 128, 32)
         self.rank, self.world, self.device = rank, world, device
@@ -367,6 +375,7 @@ class HybridWorkload:
                                 f"gathered buffers in place, MaxSim by row owner + NCCL max-reduce, replicated fusion") if self.world > 1 else "single GPU",
                 "l2": f"dense shard {self.N * self.d * 2 / 1e9:.1f} GB, postings {getattr(self, 'nnz', 0) * 8 / 1e9:.1f} GB >> 126 MB L2 (no flush needed)",
                 "stages_ms": getattr(self, "stages_ms", None),
+                "sm_partition": self.partition,
                 "value_definition": "weak scaling: every rank answers the whole batch against its own 1/8 shard of configs[4]; "
                                     "value = n_gpus * batch_queries * steps / time (shard-level query scans per second); "
                                     "global_queries_per_s = batch_queries * steps / time is the rate at which the n_gpus-shard corpus answers queries"}
@@ -394,13 +403,19 @@ class HybridWorkload:
         self.alg_postings = int(sum(int(df[np.unique(qt[qi[j]:qi[j + 1]])].sum()) for j in range(self.nq)))
         self.cand_owned = None
         self._stage_times()
+        self._pick_partition()
 
     def _stage_times(self):
-        """Per-stage device times of one step, run stage by stage with a synchronising event after each (outside the timed
-        region), reported in config.stages_ms.  Also counts the MaxSim candidates this rank scores."""
+        """Per-stage device times of one step with the stages ONE AFTER THE OTHER, each on the whole machine, run stage by stage
+        with a synchronising event after each (outside the timed region), reported in config.stages_ms; the library's
+        launch profiler gives every kernel family's time in that arrangement (`alone_ms`).  Also counts the MaxSim candidates
+        this rank scores."""
         torch, eng, sh = self.torch, self.engine, self.shard
         ev = lambda: torch.cuda.Event(enable_timing=True)
-        for _ in range(2):
+        sh.dense_sms = 0
+        for it in range(2):
+            if it == 1:
+                eng.prof_enable(64)
             marks = [ev() for _ in range(5)]
             marks[0].record()
             d = eng.allgather_merge(*eng.dense_topk(sh.X, self.Qd, self.kc, sh.id_base), self.kc)
@@ -416,11 +431,54 @@ class HybridWorkload:
             else:
                 eng.allgather_merge(*eng.maxsim_scan_topk(sh.tokens, None, self.Qtok, self.kc, id_base=sh.id_base), self.kc)
             marks[3].record()
+            if it == 1:
+                torch.cuda.synchronize()
+                self.alone_ms = {}
+                for name, t in eng.prof_collect():
+                    self.alone_ms[name] = self.alone_ms.get(name, 0.0) + t
+                eng.prof_enable(0)
             self.step()
             marks[4].record()
             torch.cuda.synchronize()
         self.stages_ms = {"dense+merge": marks[0].elapsed_time(marks[1]), "bm25+merge": marks[1].elapsed_time(marks[2]),
-                          "candidates+maxsim": marks[2].elapsed_time(marks[3]), "whole_step": marks[3].elapsed_time(marks[4])}
+                          "candidates+maxsim": marks[2].elapsed_time(marks[3]), "whole_step": marks[3].elapsed_time(marks[4]),
+                          "arrangement": "one after the other, each stage on the whole GPU"}
+
+    def _pick_partition(self):
+        """SM partition of the two big scans (HybridShard.dense_sms, csrc/partition.cu): `--dense-sms N` fixes it, `0` runs the
+        stages one after the other, `auto` (default) times a few splits for three steps each, outside the timed region, and
+        keeps the fastest (max over ranks)."""
+        torch, sh = self.torch, self.shard
+        import torch.distributed as dist
+        sms = self.engine._native.load().lrag_sm_count()
+        if self.dense_sms_arg != "auto":
+            sh.dense_sms = max(0, min(int(self.dense_sms_arg), sms - 8))
+            tried = None
+        else:
+            cands = [0] + [c for c in (64, 68, 72) if c < sms - 8]
+            times = []
+            for c in cands:
+                sh.dense_sms = c
+                self.step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    self.step()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1) / 3)
+            t = torch.tensor(times, dtype=torch.float64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times = t.tolist()
+            sh.dense_sms = cands[min(range(len(cands)), key=lambda i: times[i])]
+            tried = {("one after the other" if c == 0 else f"dense on {c} SMs"): round(ms, 2) for c, ms in zip(cands, times)}
+        D = sh.dense_sms
+        self.partition = {"dense_sms": D, "bm25_sms": sms - D if D else 0, "sms": sms, "tried_ms_per_step": tried,
+                          "what": ("dense scan and BM25 scan side by side on disjoint SM sets (lrag_sm_reserve): the power-capped dense stage "
+                                   "no longer leaves the low-power BM25 stage a throttled clock; results are identical to the serial step")
+                                  if D else "stages one after the other, each on the whole GPU"}
 
     def step(self):
         return self.shard.search_device(self.Qd, self.q_indptr, self.q_term, self.mx, self.Qtok, k=self.k, kc=self.kc,
@@ -429,6 +487,13 @@ class HybridWorkload:
     def e2e_step(self):
         return self.shard.search(self.host[0], self.host[1], self.host[2], self.mx, self.host[3], k=self.k, kc=self.kc,
                                  colbert_mode=self.colbert_mode)
+
+    def critical_kernel_ms(self, by_tag):
+        """Kernel time on the step's critical path: side-by-side scans count once (the longer one)."""
+        if self.partition and self.partition.get("dense_sms"):
+            both = ("dense_scan", "bm25_scan")
+            return max(by_tag.get(t, 0.0) for t in both) + sum(v for t, v in by_tag.items() if t not in both)
+        return sum(by_tag.values())
 
     def e2e_bytes(self):
         return sum(t.numel() * t.element_size() for t in self.host), self.nq * self.k * 12
@@ -440,13 +505,25 @@ class HybridWorkload:
         """One entry per kernel family of the step: algorithmic work per step, device time per step (summed over the family's
         launches), achieved rate and fraction of the measured peak that bounds it."""
         out = []
+        part = self.partition or {}
+        share = {"dense_scan": part.get("dense_sms", 0), "bm25_scan": part.get("bm25_sms", 0)} if part.get("dense_sms") else {}
         def entry(kernel, tag, bound, work, unit_div, unit, peak, alg, **extra):
             ms = by_tag.get(tag, 0.0)
             if ms <= 0:
                 return
             ach = work / (ms * 1e-3) / unit_div
-            out.append(dict({"kernel": kernel, "bound": bound, "kernel_ms": ms, "achieved": ach, "peak": peak, "unit": unit,
-                             "frac": ach / peak, "algorithmic": alg}, **extra))
+            e = dict({"kernel": kernel, "bound": bound, "kernel_ms": ms, "achieved": ach, "peak": peak, "unit": unit,
+                      "frac": ach / peak, "algorithmic": alg}, **extra)
+            if share.get(tag):
+                # the kernel ran on a part of the machine, side by side with the other scan: `frac` is still against the
+                # whole GPU's peak; per SM it is frac / sm_share; `alone` = the same kernel by itself on the whole GPU,
+                # measured in this run with the stages one after the other (setup, outside the timed region)
+                e["sms"], e["sm_share"] = share[tag], share[tag] / part["sms"]
+                e["frac_of_sm_share"] = e["frac"] / e["sm_share"]
+                if self.alone_ms.get(tag):
+                    a = work / (self.alone_ms[tag] * 1e-3) / unit_div
+                    e["alone"] = {"kernel_ms": self.alone_ms[tag], "achieved": a, "frac": a / peak}
+            out.append(e)
         flops = 2.0 * self.nq * self.N * self.d
         entry("dense_scan_kernel", "dense_scan", "tensor", flops, 1e12, "TFLOP/s", peaks["bf16_tflops"], f"2*nq*N*d = {flops:.3e} FLOP",
               peak_burst=peaks["bf16_tflops_burst"])
@@ -476,7 +553,8 @@ class HybridWorkload:
         top = max(stages, key=lambda e: e["kernel_ms"])
         roof = dict(top)
         roof.setdefault("traffic", None)
-        roof["kernel"] = top["kernel"] + " (longest stage of the hybrid step)"
+        roof["kernel"] = top["kernel"] + (f" on {top['sms']} of {self.partition['sms']} SMs, side by side with the other scan (longest kernel of "
+                                          f"the hybrid step)" if top.get("sms") else " (longest stage of the hybrid step)")
         roof["peak_source"] = peaks["source"] + (" (copy bandwidth)" if top["bound"] == "hbm" else " (sustained cuBLAS bf16)")
         roof["stages"] = stages
         return roof
@@ -903,7 +981,7 @@ def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks, e2
             "roofline": with_burst(roof, peaks),
             "global_queries_per_s": wl.nq * steps / (ms * 1e-3),
             "kernel_ms_per_step": by_tag,
-            "rest_of_step_ms": ms / steps - sum(by_tag.values())}
+            "rest_of_step_ms": ms / steps - (wl.critical_kernel_ms(by_tag) if hasattr(wl, "critical_kernel_ms") else sum(by_tag.values()))}
     if e2e:
         h2d, d2h = wl.e2e_bytes()
         line["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -1067,6 +1145,8 @@ def main():
     ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
                     help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense-sms", default="auto", help="hybrid workload: SMs of the dense scan when it runs side by side with the BM25 "
+                    "scan (the rest go to BM25); 0 = one after the other; auto = time a few splits and keep the fastest")
     ap.add_argument("--no-side-blocks", action="store_true",
                     help="default workload only: skip parity_check / strong / kernels / api (profiling runs)")
     args = ap.parse_args()

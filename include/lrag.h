@@ -82,6 +82,12 @@ size_t lrag_dense_topk_workspace_bytes(int64_t N, int d, int nq, int k);
 int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void* Q, int nq, int k,
                          int64_t id_base, float* out_score, int64_t* out_id, void* ws,
                          size_t ws_bytes, lrag_stream_t stream);
+/* The same scan confined to `max_ctas` SMs (0 = all of them), for a stage that shares the machine with another
+ * persistent kernel (see lrag_sm_reserve).  Results do not depend on max_ctas; the workspace does. */
+size_t lrag_dense_topk_workspace_bytes_part(int64_t N, int d, int nq, int k, int max_ctas);
+int lrag_dense_topk_bf16_part(const void* X, int64_t N, int d, const void* Q, int nq, int k,
+                              int64_t id_base, int max_ctas, float* out_score, int64_t* out_id, void* ws,
+                              size_t ws_bytes, lrag_stream_t stream);
 /* CUDA-core cross-check of the same contract (fp32 FMA, materialises [nq, N] scores in
  * the workspace).  Test instrument for the tcgen05 path; small shapes only. */
 size_t lrag_dense_topk_ref_workspace_bytes(int64_t N, int d, int nq, int k);
@@ -170,6 +176,29 @@ int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id, const flo
                          const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                          int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
                          int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
+/* The same with a grid of at most `max_ctas` CTAs (0 = two per SM over the whole machine) whose CTAs add one to
+ * *start_counter (may be NULL) as they become resident: the BM25 side of an SM partition (lrag_sm_reserve).
+ * lrag_bm25_grid tells how many CTAs such a call launches.  Results do not depend on max_ctas. */
+int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_ctas);
+int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
+                        const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
+                        const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                        int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_ctas,
+                        unsigned long long* start_counter, float* out_score, int64_t* out_id, void* ws,
+                        size_t ws_bytes, lrag_stream_t stream);
+
+/* ---------------------------------------------------------------------------------
+ * SM partition for two persistent scans that run side by side (no reference counterpart: the reference runs its
+ * channels one after the other on the CPU, legalrag/retrieval/hybrid_retriever.py:295-299).  The dense scan
+ * (192 KB of shared memory per CTA) and the BM25 scan (2 x 113 KB per SM) cannot share an SM.  lrag_sm_reserve parks
+ * one CTA holding 200 KB of shared memory on `ctas` SMs until *counter >= target (or `timeout_ms` passes): launch
+ * it first, then lrag_bm25_topk_part on a second stream with max_ctas = 2 x (SMs - ctas) and the same counter
+ * (target = counter value before + lrag_bm25_grid(...)); its CTAs can only land on the other SMs.  A third stream
+ * that waits for the reservation then runs lrag_dense_topk_bf16_part with max_ctas = ctas on exactly the SMs the
+ * reservation gives back.  On a power-capped board the two stages side by side draw a steady load at one clock;
+ * one after the other the low-power stage inherits the clock the high-power stage was throttled to. */
+int lrag_sm_reserve(int ctas, const unsigned long long* counter, unsigned long long target, int timeout_ms,
+                    lrag_stream_t stream);
 
 /* ---------------------------------------------------------------------------------
  * ColBERT channel.  Replaces the scoring inside `Searcher.search(query, k)` at

@@ -33,6 +33,8 @@ SIGNATURES = {
     "lrag_launch_count": (C.c_longlong, []),
     "lrag_dense_topk_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
     "lrag_dense_topk_bf16": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "lrag_dense_topk_workspace_bytes_part": (_c_sz, [_c_i64, _c_int, _c_int, _c_int, _c_int]),
+    "lrag_dense_topk_bf16_part": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_int, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_dense_topk_ref_workspace_bytes": (_c_sz, [_c_i64, _c_int, _c_int, _c_int]),
     "lrag_dense_topk_bf16_ref": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_int, _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_dense_gather_scores_bf16": (_c_int, [_c_p, _c_i64, _c_int, _c_p, _c_int, _c_p, _c_int, _c_p, _c_p]),
@@ -46,6 +48,10 @@ SIGNATURES = {
                                 C.c_float, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "lrag_bm25_topk_dense": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_int,
                                       _c_i64, _c_int, C.c_float, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "lrag_bm25_grid": (_c_int, [_c_i64, _c_int, _c_int, _c_i64, _c_int]),
+    "lrag_bm25_topk_part": (_c_int, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_p, _c_p, _c_int, _c_i64, _c_i64, _c_int,
+                                     _c_i64, _c_int, C.c_float, _c_int, _c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "lrag_sm_reserve": (_c_int, [_c_int, _c_p, C.c_ulonglong, _c_int, _c_p]),
     "lrag_maxsim_rerank_workspace_bytes": (_c_sz, [_c_int, _c_int, _c_int]),
     "lrag_maxsim_rerank_bf16": (_c_int, [_c_p, _c_p, _c_i64, _c_int, _c_int, _c_p, _c_int, _c_int, _c_p, _c_int, _c_int,
                                          _c_i64, _c_p, _c_p, _c_p, _c_sz, _c_p]),

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liblrag.so"
-SOURCES = ["common.cu", "select.cu", "dense.cu", "gather.cu", "bm25.cu", "maxsim.cu", "maxsim_scan.cu", "fuse.cu"]
+SOURCES = ["common.cu", "select.cu", "dense.cu", "gather.cu", "bm25.cu", "maxsim.cu", "maxsim_scan.cu", "fuse.cu", "partition.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -119,6 +119,7 @@ struct Bm25Params {
   int nq, k, nonneg, S, cap, P, TS, item_slabs, steps, nc;
   int slab;                        // docs per slab (multiple of BM25_SLAB_STEP)
   float impact_bound;              // >= max |impact| over the index
+  unsigned long long* start_counter;   // every CTA counts itself in when it starts (partition.cu), or null
   Bm25Ws ws;
 };
 
@@ -722,6 +723,7 @@ bm25_scan_kernel(const __grid_constant__ Bm25Params p) {
     fence_barrier_init();
   }
   if (tid < BM25_TABS) { sh.tab[tid].tag = 0; sh.tab[tid].arrived = BM25_WARPS; }
+  if (tid == 0 && p.start_counter) atomicAdd(p.start_counter, 1ull);      // this CTA is resident
   __syncthreads();                 // (the accumulators are initialised at the beginning of every slab)
   if (warp == BM25_CONSUMERS / 32 + 1) {
     // ===================== bounds warp =====================
@@ -1188,6 +1190,33 @@ extern "C" int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id
                                     const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                                     int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
                                     int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
+  return lrag_bm25_topk_part(indptr, doc_id, impact, V, nnz, dense_term, dense_rows, n_dense, dense_stride, q_indptr, q_term, nq,
+                             max_query_terms, N, k, id_base, nonneg, impact_bound, 0, nullptr, out_score, out_id, ws, ws_bytes, stream_);
+}
+
+// CTAs the scan launches when it may use at most `max_ctas` (0 = the whole machine)
+static unsigned long long bm25_grid(const Bm25Plan& pl, int max_ctas, int occ) {
+  unsigned long long grid = (unsigned long long)occ * sm_count();
+  if (max_ctas > 0 && (unsigned long long)max_ctas < grid) grid = max_ctas;
+  if (grid > pl.total_items) grid = pl.total_items;
+  return grid;
+}
+
+extern "C" int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_ctas) {
+  if (N < 0 || nq <= 0 || k <= 0 || k > LRAG_MAX_K || max_ctas < 0 || !initialised()) return 0;
+  const Bm25Plan pl = bm25_plan(N, nq, k, max_query_terms, sm_count());
+  int occ = 0;
+  cudaFuncSetAttribute(bm25_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem) != cudaSuccess || occ < 1) return 0;
+  return int(bm25_grid(pl, max_ctas, occ));
+}
+
+extern "C" int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
+                                   const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
+                                   const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
+                                   int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_ctas,
+                                   unsigned long long* start_counter, float* out_score,
+                                   int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LRAG_REQUIRE(n_dense >= 0 && n_dense <= 32 && (n_dense == 0 || (dense_term && dense_rows && dense_stride >= N && dense_stride % 32 == 0 &&
                                                 (reinterpret_cast<uintptr_t>(dense_rows) & 127) == 0)),
@@ -1228,6 +1257,8 @@ extern "C" int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id
   p.ws.out_keys = reinterpret_cast<uint64_t*>(w + pl.off[11]);
   p.ws.q_inv_scale = reinterpret_cast<float*>(w + pl.off[12]);
   p.impact_bound = impact_bound;
+  p.start_counter = start_counter;
+  LRAG_REQUIRE(max_ctas >= 0, "bm25_topk: max_ctas=%d must be >= 0 (0 = the whole machine)", max_ctas);
 
   static size_t smem_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
   const int dev = device_slot();
@@ -1238,8 +1269,7 @@ extern "C" int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id
   int occ = 0;
   LRAG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem));
   LRAG_REQUIRE(occ >= 1, "bm25_topk: the scan kernel does not fit on an SM (smem %zu)", pl.smem);
-  unsigned long long grid = (unsigned long long)occ * sms;
-  if (grid > pl.total_items) grid = pl.total_items;
+  const unsigned long long grid = bm25_grid(pl, max_ctas, occ);
   const int prep_blocks = int(std::min<int64_t>((int64_t(nq) + 7) / 8, 4 * int64_t(sms)));
   bm25_prepare_kernel<<<prep_blocks, 256, 0, stream>>>(p);
   LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();

@@ -321,15 +321,29 @@ static DensePlan dense_plan(int64_t N, int d, int nq, int k, int sms) {
 
 using namespace lrag;
 
+// SMs the scan's persistent grid may use: all of them, or `max_ctas` of them when the scan shares the machine (partition.cu)
+static int dense_sms(int max_ctas) { const int sms = sm_count(); return max_ctas > 0 && max_ctas < sms ? max_ctas : sms; }
+
+extern "C" size_t lrag_dense_topk_workspace_bytes_part(int64_t N, int d, int nq, int k, int max_ctas) {
+  if (N < 0 || nq <= 0 || k <= 0 || d <= 0 || max_ctas < 0) return 0;
+  return dense_plan(N, d, nq, k, dense_sms(max_ctas)).total;
+}
+
 extern "C" size_t lrag_dense_topk_workspace_bytes(int64_t N, int d, int nq, int k) {
-  if (N < 0 || nq <= 0 || k <= 0 || d <= 0) return 0;
-  return dense_plan(N, d, nq, k, sm_count()).total;
+  return lrag_dense_topk_workspace_bytes_part(N, d, nq, k, 0);
 }
 
 extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void* Q, int nq, int k,
                                     int64_t id_base, float* out_score, int64_t* out_id, void* ws,
                                     size_t ws_bytes, lrag_stream_t stream_) {
+  return lrag_dense_topk_bf16_part(X, N, d, Q, nq, k, id_base, 0, out_score, out_id, ws, ws_bytes, stream_);
+}
+
+extern "C" int lrag_dense_topk_bf16_part(const void* X, int64_t N, int d, const void* Q, int nq, int k,
+                                         int64_t id_base, int max_ctas, float* out_score, int64_t* out_id, void* ws,
+                                         size_t ws_bytes, lrag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LRAG_REQUIRE(max_ctas >= 0, "dense_topk: max_ctas=%d must be >= 0 (0 = every SM)", max_ctas);
   LRAG_REQUIRE(initialised(), "lrag_init has not been called");
   LRAG_REQUIRE(nq > 0 && k > 0 && k <= LRAG_MAX_K, "dense_topk: need nq > 0 and 1 <= k <= %d (nq=%d k=%d)", LRAG_MAX_K, nq, k);
   LRAG_REQUIRE(N >= 0 && N < (int64_t(1) << 31), "dense_topk: N=%lld out of range for one shard", (long long)N);
@@ -337,7 +351,7 @@ extern "C" int lrag_dense_topk_bf16(const void* X, int64_t N, int d, const void*
   LRAG_REQUIRE(Q && out_score && out_id && (X || N == 0), "dense_topk: null pointer");
   LRAG_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0,
                "dense_topk: X and Q must be 16-byte aligned");
-  const DensePlan pl = dense_plan(N, d, nq, k, sm_count());
+  const DensePlan pl = dense_plan(N, d, nq, k, dense_sms(max_ctas));
   if (ws_bytes < pl.total || !ws) { set_error("dense_topk: workspace %zu < required %zu", ws_bytes, pl.total); return LRAG_ENOSPC; }
 
   DenseParams p;

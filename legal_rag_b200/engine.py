@@ -46,12 +46,13 @@ def _out(nq: int, k: int, device):
 # ------------------------------------------------------------------------------------------------
 # dense
 # ------------------------------------------------------------------------------------------------
-def dense_topk(X: torch.Tensor, Q: torch.Tensor, k: int, id_base: int = 0, *, reference_kernel: bool = False
-               ) -> Tuple[torch.Tensor, torch.Tensor]:
+def dense_topk(X: torch.Tensor, Q: torch.Tensor, k: int, id_base: int = 0, *, reference_kernel: bool = False,
+               max_ctas: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Exact flat inner-product top-k: X [N, d] bf16 corpus shard, Q [nq, d] bf16 queries.
 
     reference_kernel=True runs the CUDA-core cross-check kernel instead of the tcgen05 scan
-    (tests only; it materialises the [nq, N] score matrix)."""
+    (tests only; it materialises the [nq, N] score matrix).  max_ctas > 0 confines the scan to that many SMs
+    (HybridShard's side-by-side scans); the result does not depend on it."""
     lib = _native.init(X.device.index)
     X = _need(X, torch.bfloat16, 2, "X")
     Q = _need(Q, torch.bfloat16, 2, "Q")
@@ -64,8 +65,9 @@ def dense_topk(X: torch.Tensor, Q: torch.Tensor, k: int, id_base: int = 0, *, re
         ws = _ws(lib.lrag_dense_topk_ref_workspace_bytes(N, d, nq, k), X.device)
         rc = lib.lrag_dense_topk_bf16_ref(_ptr(X), N, d, _ptr(Q), nq, k, id_base, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
     else:
-        ws = _ws(lib.lrag_dense_topk_workspace_bytes(N, d, nq, k), X.device)
-        rc = lib.lrag_dense_topk_bf16(_ptr(X), N, d, _ptr(Q), nq, k, id_base, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+        ws = _ws(lib.lrag_dense_topk_workspace_bytes_part(N, d, nq, k, int(max_ctas)), X.device)
+        rc = lib.lrag_dense_topk_bf16_part(_ptr(X), N, d, _ptr(Q), nq, k, id_base, int(max_ctas), _ptr(s), _ptr(i), _ptr(ws), ws.numel(),
+                                           _stream())
     check(rc, "lrag_dense_topk_bf16")
     return s, i
 
@@ -164,11 +166,11 @@ class Bm25DeviceIndex:
         handful of terms carry most of the posting volume).  The scan initialises every slab of accumulators from the rows
         of the query's dense terms -- vector loads and one 16-byte store per four documents -- instead of zeroing it and
         adding those terms posting by posting with shared-memory atomics.  4 N bytes per row; called once, on first use,
-        by bm25_topk.  Default threshold: LRAG_BM25_DENSE_MIN_DENSITY or 0.2 (> 1 disables).  Returns the number of rows."""
+        by bm25_topk.  Default threshold: LRAG_BM25_DENSE_MIN_DENSITY or 0.5 (> 1 disables).  Returns the number of rows."""
         import os
         self._dense_built = True
         if min_density is None:
-            min_density = float(os.environ.get("LRAG_BM25_DENSE_MIN_DENSITY", "0.2"))
+            min_density = float(os.environ.get("LRAG_BM25_DENSE_MIN_DENSITY", "0.5"))
         max_rows = min(int(max_rows), 32)
         N = int(self.n_docs)
         self.dense_term, self.dense_rows = None, None
@@ -203,8 +205,11 @@ def bm25_set_item_slabs(slabs: int) -> None:
     check(_native.load().lrag_bm25_set_item_slabs(int(slabs)), "lrag_bm25_set_item_slabs")
 
 
-def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int, k: int):
-    """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV)."""
+def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int, k: int, *,
+              max_ctas: int = 0, start_counter: Optional[torch.Tensor] = None):
+    """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV).  max_ctas > 0 limits the scan's
+    grid and start_counter (int64 [1]) is incremented by every CTA as it starts (HybridShard's side-by-side scans);
+    the result depends on neither."""
     lib = _native.init(index.indptr.device.index)
     dev = index.indptr.device
     q_indptr = _need(q_indptr, torch.int64, 1, "q_indptr")
@@ -217,11 +222,11 @@ def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tens
     if not index._dense_built:
         index.build_dense_rows()
     n_dense = 0 if index.dense_term is None else int(index.dense_term.numel())
-    rc = lib.lrag_bm25_topk_dense(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, index.nnz,
-                                  _ptr(index.dense_term) if n_dense else None, _ptr(index.dense_rows) if n_dense else None, n_dense,
-                                  int(index.dense_rows.shape[1]) if n_dense else 0, _ptr(q_indptr),
-                            _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
-                            index.impact_bound, _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+    rc = lib.lrag_bm25_topk_part(_ptr(index.indptr), _ptr(index.doc_id), _ptr(index.impact), index.vocab, index.nnz,
+                                 _ptr(index.dense_term) if n_dense else None, _ptr(index.dense_rows) if n_dense else None, n_dense,
+                                 int(index.dense_rows.shape[1]) if n_dense else 0, _ptr(q_indptr),
+                                 _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
+                                 index.impact_bound, int(max_ctas), _ptr(start_counter), _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
     check(rc, "lrag_bm25_topk")
     return s, i
 
@@ -464,6 +469,45 @@ class HybridShard:
     tok_row_base: int = 0
     tok_rows_total: int = 0
     group: object = None
+    # > 0: the dense scan and the BM25 scan run side by side, the dense scan on this many SMs and BM25 on the rest
+    # (lrag_sm_reserve, csrc/partition.cu); 0: one after the other, each on the whole machine
+    dense_sms: int = 0
+
+    def _scans_side_by_side(self, Qd, q_indptr, q_term, max_query_terms: int, kc: int):
+        """Dense scan on `dense_sms` SMs and BM25 scan on the others at the same time.  One after the other the power-capped
+        dense stage throttles the SM clock and the low-power BM25 stage inherits it (the governor raises it again only
+        slowly): the step averages ~80 % of the board's power budget.  Side by side the load is steady.  Streams: a
+        reservation parks on the dense scan's SMs; BM25 (second stream) fills the rest and counts its CTAs in; the
+        reservation ends when all of them are resident; the dense scan (main stream, waiting for the reservation) gets
+        exactly the SMs it gave back."""
+        lib = _native.init(self.X.device.index)
+        dev = self.X.device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side", None) is None:
+            self._side, self._resv = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            self._counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._started = 0
+        sms = int(lib.lrag_sm_count())
+        D = max(1, min(int(self.dense_sms), sms - 1))
+        B = 2 * (sms - D)
+        nq = q_indptr.numel() - 1
+        self._started += int(lib.lrag_bm25_grid(self.bm25.n_docs, nq, kc, max_query_terms, B))
+        if not self.bm25._dense_built:
+            self.bm25.build_dense_rows()
+        self._side.wait_stream(main)
+        self._resv.wait_stream(main)
+        with torch.cuda.stream(self._resv):
+            check(lib.lrag_sm_reserve(D, _ptr(self._counter), self._started, 200, _stream()), "lrag_sm_reserve")
+            freed = torch.cuda.Event()
+            freed.record()
+        with torch.cuda.stream(self._side):
+            b = bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc, max_ctas=B, start_counter=self._counter)
+        main.wait_event(freed)
+        d = dense_topk(self.X, Qd, kc, self.id_base, max_ctas=D)
+        main.wait_stream(self._side)
+        for t in b:
+            t.record_stream(main)
+        return [d, b]
 
     def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
                       Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",
@@ -474,7 +518,10 @@ class HybridShard:
         shard is scored by the batched full-corpus kernel; needs one token row per document (no id aliasing)."""
         import torch.distributed as dist
         # local scans first, one exchange for all channels afterwards
-        local = [dense_topk(self.X, Qd, kc, self.id_base), bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc)]
+        if self.dense_sms > 0:
+            local = self._scans_side_by_side(Qd, q_indptr, q_term, max_query_terms, kc)
+        else:
+            local = [dense_topk(self.X, Qd, kc, self.id_base), bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc)]
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, w_colbert=w_colbert, **fuse_kw)
         scan = colbert_mode == "scan" and self.tokens is not None and Qtok is not None
         if scan:

@@ -579,6 +579,33 @@ def test_hybrid_shard_matches_oracle_pipeline(eng):
                           k, 2e-3, what="hybrid-colbert-scan")
 
 
+def test_side_by_side_scans_equal_the_serial_step(eng):
+    """HybridShard.dense_sms > 0: the dense scan confined to that many SMs and the BM25 scan on the others at the same time
+    (lrag_sm_reserve / *_part entry points) return bit for bit what the two scans return one after the other, for several
+    splits, repeated calls (the start counter accumulates) and a BM25 grid smaller than its share of the machine."""
+    rng = np.random.default_rng(5)
+    N, d, V, nq, kc, k = 60_000, 256, 5000, 300, 50, 20
+    Xd, _ = _bf16(_unit(rng, (N, d)))
+    Qd, _ = _bf16(_unit(rng, (nq, d)))
+    from legal_rag_b200 import synth
+    index, _ = synth.bm25_synthetic_index(N, V, 3, "cuda", mean_len=20.0)
+    qi, qt, mx = synth.bm25_synthetic_queries(nq, V, 4, "cuda")
+    shard = eng.HybridShard(Xd, index)
+    ref = shard.search_device(Qd, qi, qt, mx, None, k=k, kc=kc)
+    d0 = eng.dense_topk(Xd, Qd, kc)
+    b0 = eng.bm25_topk(index, qi, qt, mx, kc)
+    for D in (68, 8, 140, 64):
+        shard.dense_sms = D
+        for _ in range(3):
+            s, i = shard.search_device(Qd, qi, qt, mx, None, k=k, kc=kc)
+            assert torch.equal(s, ref[0]) and torch.equal(i, ref[1]), f"dense on {D} SMs changed the fused result"
+        d1 = eng.dense_topk(Xd, Qd, kc, max_ctas=D)
+        b1 = eng.bm25_topk(index, qi, qt, mx, kc, max_ctas=2 * (148 - D))
+        assert torch.equal(d0[0], d1[0]) and torch.equal(d0[1], d1[1]), f"dense scan on {D} SMs changed its result"
+        assert torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1]), f"BM25 scan on {2 * (148 - D)} CTAs changed its result"
+    torch.cuda.synchronize()
+
+
 # ---------------------------------------------------------------- gathered inner products (graph-expansion scoring)
 @pytest.mark.parametrize("N,d,nq,C", [(500, 768, 1, 800), (64, 64, 3, 10), (3000, 1024, 17, 33), (10, 8, 2, 5)])
 def test_gather_scores_match_numpy(eng, N, d, nq, C):
