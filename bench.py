@@ -455,7 +455,7 @@ class HybridWorkload:
             sh.dense_sms = max(0, min(int(self.dense_sms_arg), sms - 8))
             tried = None
         else:
-            cands = [0] + [c for c in (64, 68, 72) if c < sms - 8]
+            cands = [0] + [c for c in (64, 68, 70, 72, 76) if c < sms - 8]
             times = []
             for c in cands:
                 sh.dense_sms = c
