@@ -421,7 +421,10 @@ __device__ __forceinline__ float4 ldg_stream_f32x4(const float* p) {
 // One pass of a slab's initialisation over one dense row: acc[d] (+)= rn(row[d] * ms).  A thread owns the int4 groups
 // tid, tid + 512, ...: plain 16-byte stores, no atomics; BM25_INIT_BATCH row loads are in flight per thread.  `lim` =
 // floats of the row from the slab's first doc on (multiple of 4).  The last pass checks the sums against the note threshold.
-constexpr int BM25_INIT_BATCH = 4;
+#ifndef LRAG_BM25_INIT_BATCH
+#define LRAG_BM25_INIT_BATCH 4
+#endif
+constexpr int BM25_INIT_BATCH = LRAG_BM25_INIT_BATCH;
 template <bool FIRST>
 __device__ __forceinline__ bool bm25_init_pass(Bm25Shared& sh, int4* a4, int iters, const float* row, float ms, int lim, int slab0,
                                                int thr_i, bool last, int hb) {
