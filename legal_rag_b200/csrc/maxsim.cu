@@ -53,6 +53,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   uint64_t* afull_bar = bars + 16;                         // [2]
   uint64_t* aempty_bar = bars + 18;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  volatile int* a_nv = reinterpret_cast<volatile int*>(bars + 21);   // [2] valid candidates of the item in A buffer ab; -1 = no more items
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,19 +74,33 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // this lane's candidate row of item `it` (-1: no such slot).  Every role loads the NEXT item's rows while it works on the
+  // current one, so the load's latency never sits in front of an item.
+  auto lane_row = [&](int64_t it) -> int64_t {
+    if (it >= p.items) return -1;
+    const int q = int(it / p.chunks);
+    const int c0 = int(it % p.chunks) * MS_CHUNK;
+    return (lane < min(MS_CHUNK, p.C - c0)) ? p.cand[size_t(q) * p.C + c0 + lane] : int64_t(-1);
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp reads candidate ids, lane 0 issues) ============
+    // Skipped slots (row < 0 or past the store: padding, or candidates another shard owns) never enter the pipeline: the three
+    // roles derive the same mask of valid slots from the candidate ids and count stages over valid slots only; an item
+    // without a valid slot costs nothing.  (The first version pushed row 0 through the ring for a skipped slot, so a shard
+    // that owns 1/8 of the candidates paid for all of them.)
     uint32_t n = 0, itc = 0;
-    for (int64_t it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
+    int64_t row_next = lane_row(blockIdx.x);
+    for (int64_t it = blockIdx.x; it < p.items; it += gridDim.x) {
       const int q = int(it / p.chunks);
-      const int c0 = int(it % p.chunks) * MS_CHUNK;
-      const int nc = min(MS_CHUNK, p.C - c0);
-      int64_t row = (lane < nc) ? p.cand[size_t(q) * p.C + c0 + lane] : -1;
-      if (row < 0 || row >= p.Nd) row = 0;   // skipped slot: keep the pipeline uniform, result is discarded
+      const int64_t row = row_next;
+      row_next = lane_row(it + gridDim.x);
+      const uint32_t vm = __ballot_sync(0xffffffffu, row >= 0 && row < p.Nd);
+      if (vm == 0) continue;
       const uint32_t ab = itc & 1;
       if (lane == 0) {
         mbar_wait_spin(&aempty_bar[ab], ((itc >> 1) & 1) ^ 1);
+        a_nv[ab] = __popc(vm);                                   // read by the MMA thread behind the barrier
         mbar_arrive_expect_tx(&afull_bar[ab], MS_A_BYTES);
         uint8_t* a = a_buf + ab * MS_A_BYTES;
 #pragma unroll
@@ -94,8 +109,8 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           for (int r = 0; r < 4; ++r)
             tma_load_2d(a + h * (MS_A_BYTES / 2) + r * 4096, &tmap_q, &afull_bar[ab], h * 64, q * p.Lq);
       }
-      for (int c = 0; c < nc; ++c, ++n) {
-        const int64_t rw = __shfl_sync(0xffffffffu, row, c);
+      for (uint32_t m = vm; m; m &= m - 1, ++n) {
+        const int64_t rw = __shfl_sync(0xffffffffu, row, __ffs(m) - 1);
         if (lane == 0) {
           const uint32_t s = n % NS, use = n / NS;
           mbar_wait_spin(&empty_bar[s], (use & 1) ^ 1);
@@ -105,19 +120,26 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           tma_load_2d(b + stage_bytes / 2, &tmap_d, &full_bar[s], 64, int32_t(rw * p.Ld));
         }
       }
+      ++itc;
+    }
+    if (lane == 0) {                                             // end marker for the MMA thread
+      const uint32_t ab = itc & 1;
+      mbar_wait_spin(&aempty_bar[ab], ((itc >> 1) & 1) ^ 1);
+      a_nv[ab] = -1;
+      mbar_arrive(&afull_bar[ab]);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
+    // ===================== MMA issuer (one thread; the producer tells it how many candidates an item holds) ==========
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, p.Ld);
-      uint32_t n = 0, itc = 0;
-      for (int64_t it = blockIdx.x; it < p.items; it += gridDim.x, ++itc) {
-        const int c0 = int(it % p.chunks) * MS_CHUNK;
-        const int nc = min(MS_CHUNK, p.C - c0);
+      uint32_t n = 0;
+      for (uint32_t itc = 0;; ++itc) {
         const uint32_t ab = itc & 1;
         mbar_wait_spin(&afull_bar[ab], (itc >> 1) & 1);
+        const int nv = a_nv[ab];
+        if (nv < 0) break;
         const uint32_t a_addr = smem_u32(a_buf + ab * MS_A_BYTES);
-        for (int c = 0; c < nc; ++c, ++n) {
+        for (int c = 0; c < nv; ++c, ++n) {
           const uint32_t s = n % NS, use = n / NS;
           mbar_wait_spin(&tempty_bar[s], (use & 1) ^ 1);
           mbar_wait_spin(&full_bar[s], use & 1);
@@ -145,16 +167,22 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (e < NS) {
       const int nchunk = (p.Ld + 31) / 32;
       uint32_t n = 0;
+      int64_t row_next = lane_row(blockIdx.x);
       for (int64_t it = blockIdx.x; it < p.items; it += gridDim.x) {
         const int q = int(it / p.chunks);
         const int c0 = int(it % p.chunks) * MS_CHUNK;
         const int nc = min(MS_CHUNK, p.C - c0);
-        for (int c = 0; c < nc; ++c, ++n) {
+        const int64_t rowl = row_next;
+        row_next = lane_row(it + gridDim.x);
+        const bool ok = rowl >= 0 && rowl < p.Nd;
+        const uint32_t vm = __ballot_sync(0xffffffffu, ok);
+        if (e == 0 && lane < nc && !ok) p.out[size_t(q) * p.C + c0 + lane] = -INFINITY;       // skipped slots
+        for (uint32_t left = vm; left; left &= left - 1, ++n) {
           if (int(n % NS) != e) continue;
+          const int c = __ffs(left) - 1;
           const uint32_t use = n / NS;
-          const int64_t row = p.cand[size_t(q) * p.C + c0 + c];
-          const bool skip = row < 0 || row >= p.Nd;
-          const int dl = skip ? 0 : (p.doclen ? min(p.doclen[row], p.Ld) : p.Ld);
+          const int64_t row = __shfl_sync(0xffffffffu, rowl, c);
+          const int dl = p.doclen ? min(p.doclen[row], p.Ld) : p.Ld;
           mbar_wait_spin(&tfull_bar[e], use & 1);
           tc_fence_after();
           const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + e * p.col_stride;
@@ -174,7 +202,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           float sum = (lane < p.Lq) ? m : 0.f;
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0) p.out[size_t(q) * p.C + c0 + c] = skip ? -INFINITY : sum;
+          if (lane == 0) p.out[size_t(q) * p.C + c0 + c] = sum;
         }
       }
     }

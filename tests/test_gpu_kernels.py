@@ -381,21 +381,27 @@ def test_maxsim_matches_oracle(eng, Nd, Ld, Lq, nq, C, k):
     doclen[:3] = Ld
     cand = np.stack([rng.permutation(Nd)[:C] if C <= Nd else rng.integers(0, Nd, C) for _ in range(nq)]).astype(np.int64)
     cand[:, 3::17] = -1
+    if C >= 64:                      # skipped slots never enter the pipeline: a run of them, a whole 32-slot item, a whole query
+        cand[0, 5:31] = -1
+        cand[1 % nq, 32:64] = -1
+        cand[nq - 1, :] = -1
+        cand[0, 40] = Nd + 5         # past the store = skipped
     sc = eng.maxsim_scores(Dd, torch.from_numpy(doclen).cuda(), Qd, torch.from_numpy(cand).cuda()).cpu().numpy()
-    ref = omaxsim.maxsim_scores(Qr, Dr, doclen, cand)
-    assert np.isneginf(sc[cand < 0]).all()
-    ok = cand >= 0
+    cand_o = np.where(cand >= Nd, -1, cand)          # the oracle knows only -1 as "skip"
+    ref = omaxsim.maxsim_scores(Qr, Dr, doclen, cand_o)
+    assert np.isneginf(sc[(cand < 0) | (cand >= Nd)]).all()
+    ok = (cand >= 0) & (cand < Nd)
     np.testing.assert_allclose(sc[ok], ref[ok], rtol=2e-4, atol=2e-4)          # oracle A: same bf16 inputs
-    ref32 = omaxsim.maxsim_scores(Q32, D32, doclen, cand)
+    ref32 = omaxsim.maxsim_scores(Q32, D32, doclen, cand_o)
     # oracle B: fp32 inputs.  A sum of 32 signed terms can sit near zero while each term carries bf16
     # input-rounding error, hence the absolute floor
     np.testing.assert_allclose(sc[ok], ref32[ok], rtol=TAU_BF16, atol=1e-2)
     s, i = eng.maxsim_rerank(Dd, torch.from_numpy(doclen).cuda(), Qd, torch.from_numpy(cand).cuda(), k)
-    o_s, o_i = omaxsim.rerank_topk(Qr, Dr, doclen, cand, min(C, k + 20))
+    o_s, o_i = omaxsim.rerank_topk(Qr, Dr, doclen, cand_o, min(C, k + 20))
     check_topk_parity(s.cpu().numpy(), i.cpu().numpy(), o_s, o_i, k, 1e-3, what="maxsim-rerank")
     # no doclen = every token counts
     sc = eng.maxsim_scores(Dd, None, Qd, torch.from_numpy(cand).cuda()).cpu().numpy()
-    ref = omaxsim.maxsim_scores(Qr, Dr, None, cand)
+    ref = omaxsim.maxsim_scores(Qr, Dr, None, cand_o)
     np.testing.assert_allclose(sc[ok], ref[ok], rtol=2e-4, atol=2e-4)
 
 
