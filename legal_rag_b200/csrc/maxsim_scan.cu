@@ -14,6 +14,7 @@
 // similarity matrices never leave TMEM; what is written is the [nq, Nd] per-document score matrix
 // (1/4096 of the token-level products), ranked by lrag_topk_select_f32.
 // Arithmetic intensity = nq * 32 / ... >= 2048 FLOP per store byte at 64 queries: tensor-bound.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -308,9 +309,19 @@ static int scan_launch(const void* D, const int32_t* doclen, int64_t Nd, int Ld,
     attr_set[dev] = true;
   }
   const int sms = sm_count();
-  int64_t nchunks = (int64_t(sms) * 64 + p.QB - 1) / p.QB;             // about 64 units per CTA
+  int64_t nchunks = (int64_t(sms) * 64 + p.QB - 1) / p.QB;             // about 64 units per CTA ...
   if (nchunks > p.DT) nchunks = p.DT;
   p.chunk_tiles = (p.DT + nchunks - 1) / nchunks;
+  // ... but chunks small enough that the ones in flight stay in L2.  The machine works on sms / QB (+ 1) chunks at a time, and
+  // when sms is not a multiple of QB a chunk's query blocks straddle two rounds of the grid: the late ones find the chunk's
+  // tiles in L2 only if a whole round's footprint fits (55 MB chunks re-read the store 2.2 x from DRAM, ncu round 2).
+  {
+    const int64_t in_flight = (sms + p.QB - 1) / p.QB + 1;
+    const char* e = getenv("LRAG_SCAN_L2_MB");
+    const int64_t budget_tiles = (int64_t(e ? atoi(e) : 8) << 20) / SC_B_BYTES;   // 8 MB: measured best of 4 ... 96 MB at 64, 256 and 1024 queries
+    const int64_t lim = std::max<int64_t>(8, budget_tiles / in_flight);
+    if (p.chunk_tiles > lim) p.chunk_tiles = lim;
+  }
   nchunks = (p.DT + p.chunk_tiles - 1) / p.chunk_tiles;
   p.units = nchunks * p.QB;
   const int grid = int(p.units < sms ? p.units : sms);
