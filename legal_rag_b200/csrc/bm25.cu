@@ -63,7 +63,7 @@ namespace lrag {
 constexpr int BM25_CONSUMERS = LRAG_BM25_CONSUMERS;  // consumer threads
 constexpr int BM25_THREADS = BM25_CONSUMERS + 64;    // consumers, emit warp, bounds warp
 constexpr int BM25_SLAB_STEP = 4 * BM25_CONSUMERS;   // slab sizes are multiples of one int4 per consumer thread
-constexpr int BM25_SLAB_MAX = 12 * BM25_SLAB_STEP;   // 24 576 docs = 96 KB
+constexpr int BM25_SLAB_MAX = 24576 / BM25_SLAB_STEP * BM25_SLAB_STEP;   // <= 24 576 docs = 96 KB
 constexpr int BM25_MAX_GROUP = 16;                   // slabs per bounds group (fewer when a query has many terms)
 constexpr int BM25_BOUND_CAP = 17 * 32;              // ints per bounds buffer: (group + 1) * nt must fit
 constexpr int BM25_MAXT = LRAG_BM25_MAX_QUERY_TERMS;
