@@ -8,7 +8,7 @@ fmt='
 import sys,json
 for l in sys.stdin:
     if l.startswith("{"):
-        d=json.loads(l); print("ms/step %.2f stages %s kernels %s clk %s" % (d["ms_per_step"], {k: round(v,2) for k,v in d["config"]["stages_ms"].items()}, {k: round(v,2) for k,v in d["kernel_ms_per_step"].items()}, d["clocks"]["sm_mhz"]))
+        d=json.loads(l); print("ms/step %.2f stages %s kernels %s clk %s" % (d["ms_per_step"], {k: round(v,2) for k,v in d["config"]["stages_ms"].items() if isinstance(v, float)}, {k: round(v,2) for k,v in d["kernel_ms_per_step"].items()}, d["clocks"]["sm_mhz"]))
 '
 for dens in $DENS; do
   echo "== hybrid step, BM25 dense rows at min density $dens"
