@@ -528,6 +528,9 @@ __device__ __noinline__ int bm25_slab_end(const Bm25Params& p, Bm25Shared& sh, i
     if (lds_volatile(&sh.drained) != seq) {
       const long long t0 = clock64();
       while (lds_volatile(&sh.drained) != seq) {
+#ifdef LRAG_BM25_DRAIN_SLEEP_NS
+        __nanosleep(LRAG_BM25_DRAIN_SLEEP_NS);
+#endif
         if (clock64() - t0 > 20000000000LL) { printf("lrag: bm25 hot-list wait timed out (block %d thread %d)\n", blockIdx.x, tid); __trap(); }
       }
     }

@@ -612,6 +612,29 @@ def test_side_by_side_scans_equal_the_serial_step(eng):
     torch.cuda.synchronize()
 
 
+def test_sm_reservation_times_out_when_its_partner_never_comes(eng):
+    """lrag_sm_reserve holds its SMs until the counter reaches the target -- or the timeout passes: a reservation whose BM25
+    launch failed must not hold a part of the machine for ever; one whose target is already reached exits at once."""
+    import time
+    from legal_rag_b200 import _native
+    lib = _native.init(0)
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    assert lib.lrag_sm_reserve(8, counter.data_ptr(), 5, 20, stream) == 0          # never reached: 20 ms
+    torch.cuda.synchronize()
+    waited = time.perf_counter() - t0
+    assert 0.005 < waited < 1.0, waited
+    counter.fill_(5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    assert lib.lrag_sm_reserve(8, counter.data_ptr(), 5, 2000, stream) == 0        # already reached
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 0.5
+    assert lib.lrag_sm_reserve(1000, counter.data_ptr(), 5, 20, stream) != 0       # more SMs than the device has
+
+
 # ---------------------------------------------------------------- gathered inner products (graph-expansion scoring)
 @pytest.mark.parametrize("N,d,nq,C", [(500, 768, 1, 800), (64, 64, 3, 10), (3000, 1024, 17, 33), (10, 8, 2, 5)])
 def test_gather_scores_match_numpy(eng, N, d, nq, C):
