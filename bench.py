@@ -455,25 +455,9 @@ class HybridWorkload:
             sh.dense_sms = max(0, min(int(self.dense_sms_arg), sms - 8))
             tried = None
         else:
-            cands = [0] + [c for c in (64, 68, 70, 72, 76) if c < sms - 8]
-            times = []
-            for c in cands:
-                sh.dense_sms = c
-                self.step()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    self.step()
-                e1.record()
-                torch.cuda.synchronize()
-                times.append(e0.elapsed_time(e1) / 3)
-            t = torch.tensor(times, dtype=torch.float64, device=self.device)
-            if self.world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            times = t.tolist()
-            sh.dense_sms = cands[min(range(len(cands)), key=lambda i: times[i])]
-            tried = {("one after the other" if c == 0 else f"dense on {c} SMs"): round(ms, 2) for c, ms in zip(cands, times)}
+            timed = sh.tune_partition(self.Qd, self.q_indptr, self.q_term, self.mx, self.Qtok, k=self.k, kc=self.kc,
+                                      colbert_mode=self.colbert_mode)
+            tried = {("one after the other" if c == 0 else f"dense on {c} SMs"): round(ms, 2) for c, ms in timed.items()}
         D = sh.dense_sms
         self.partition = {"dense_sms": D, "bm25_sms": sms - D if D else 0, "sms": sms, "tried_ms_per_step": tried,
                           "what": ("dense scan and BM25 scan side by side on disjoint SM sets (lrag_sm_reserve): the power-capped dense stage "

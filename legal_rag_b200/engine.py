@@ -509,6 +509,34 @@ class HybridShard:
             t.record_stream(main)
         return [d, b]
 
+    def tune_partition(self, Qd, q_indptr, q_term, max_query_terms: int, Qtok=None, *, candidates=(0, 64, 68, 70, 72, 76),
+                       steps: int = 3, **search_kw):
+        """Times the batched step on a representative batch for several values of `dense_sms` (0 = scans one after the other)
+        and keeps the fastest.  The right split depends on the workload -- how much tensor work the dense scan has against
+        how many postings the BM25 scan walks -- and on the board's power limit, so it is measured, not guessed.  With
+        several ranks the slowest rank's time decides (the ranks meet in every step).  Returns {dense_sms: ms per step}."""
+        import torch.distributed as dist
+        sms = int(_native.init(self.X.device.index).lrag_sm_count())
+        cands = [int(c) for c in candidates if 0 <= int(c) <= sms - 8]
+        times = []
+        for c in cands:
+            self.dense_sms = c
+            self.search_device(Qd, q_indptr, q_term, max_query_terms, Qtok, **search_kw)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                self.search_device(Qd, q_indptr, q_term, max_query_terms, Qtok, **search_kw)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / steps)
+        t = torch.tensor(times, dtype=torch.float64, device=self.X.device)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        times = t.tolist()
+        self.dense_sms = cands[min(range(len(cands)), key=lambda i: times[i])]
+        return dict(zip(cands, times))
+
     def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
                       Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",
                       w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, colbert_mode: str = "rerank",
