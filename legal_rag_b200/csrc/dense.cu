@@ -39,6 +39,7 @@ struct DenseParams {
   int slots;         // (QB / g) * 128 candidate buffers per CTA
   int cap;           // entries per candidate buffer
   int debug;         // 0 normal; 1 = TMA only (no MMA, no epilogue); 2 = TMA + MMA, epilogue skipped (timing experiments)
+  int x_evict_first; // corpus tiles are loaded with an L2 evict-first hint (the scan shares the machine with the BM25 scan)
   uint32_t* thr;     // [QB*128] orderable k-th best score so far, per query
   int32_t* cnt;      // [grid * slots]
   uint64_t* buf;     // [grid * slots * cap]
@@ -86,6 +87,7 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint64_t x_policy = l2_policy_evict_first();
       for (int64_t t = p.t_begin + blockIdx.x; t < p.t_end; t += gridDim.x) {
         const int qb = int(t % p.QB);
         const int64_t dt = t / p.QB;
@@ -95,7 +97,8 @@ dense_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           uint8_t* sb = sa + DENSE_A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], DENSE_STAGE_BYTES);
           tma_load_2d(sa, &tmap_q, &full_bar[stage], kb * DENSE_BK, qb * DENSE_BM);
-          tma_load_2d(sb, &tmap_x, &full_bar[stage], kb * DENSE_BK, int32_t(dt * DENSE_BN));
+          if (p.x_evict_first) tma_load_2d_hint(sb, &tmap_x, &full_bar[stage], kb * DENSE_BK, int32_t(dt * DENSE_BN), x_policy);
+          else tma_load_2d(sb, &tmap_x, &full_bar[stage], kb * DENSE_BK, int32_t(dt * DENSE_BN));
           if (++stage == DENSE_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -356,6 +359,7 @@ extern "C" int lrag_dense_topk_bf16_part(const void* X, int64_t N, int d, const 
 
   DenseParams p;
   { const char* dbg = getenv("LRAG_DENSE_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+  { const char* ev = getenv("LRAG_DENSE_X_EVICT_FIRST"); p.x_evict_first = ev ? atoi(ev) : 0; }
   p.N = N; p.nq = nq; p.d = d; p.k = k; p.QB = pl.QB; p.DT = pl.DT; p.g = pl.g; p.slots = pl.slots; p.cap = pl.cap;
   uint8_t* w = static_cast<uint8_t*>(ws);
   p.thr = reinterpret_cast<uint32_t*>(w + pl.off_thr);
