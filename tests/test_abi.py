@@ -91,3 +91,36 @@ def test_product_code_never_touches_the_oracle():
                         re.search(r"(__import__|import_module)\(\s*['\"]oracle", src):
                     bad.append(fn)
     assert not bad, bad
+
+
+def _build_c_smoke(tmp_path, lib_path):
+    """gcc-compiles tests/c_abi/smoke.c (a plain-C caller of the ABI) against the header and the library."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime_api.h")):
+        pytest.skip("gcc or the CUDA runtime headers are not installed")
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(os.path.abspath(str(lib_path)))
+    cmd = ["gcc", "-O1", "-Wall", "-Werror", os.path.join(root, "tests", "c_abi", "smoke.c"), "-I" + os.path.join(root, "include"),
+           "-I" + os.path.join(cuda, "include"), "-L" + libdir, "-llrag", "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_a_plain_c_caller_compiles_and_links_against_the_header(tmp_path, lib_path):
+    """The boundary is a C ABI: a C translation unit that includes lrag.h and calls the entry points with device pointers
+    must compile with -Wall -Werror and link against liblrag.so (it is RUN by the GPU suite)."""
+    _build_c_smoke(tmp_path, lib_path)
+
+
+@pytest.mark.gpu
+def test_a_plain_c_caller_gets_the_right_answers(tmp_path, lib_path):
+    import subprocess
+    exe = _build_c_smoke(tmp_path, lib_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c abi smoke ok" in r.stdout
