@@ -326,10 +326,20 @@ topk_stream_kernel(const float* __restrict__ S, int64_t ld, int64_t N, int k, co
       }
       row_start = false;
       if (vmax >= f.thr_s) {
+        // Which of the thread's eight scores reach the threshold, then one pass of the append code per hit of the warp's
+        // busiest lane (one, as a rule) with the score picked by a select tree -- not one pass per SLOT: a warp runs the
+        // body whenever any of its lanes has a hit, which early in a row is every trip.
         const uint32_t col0 = uint32_t(tr) * STREAM_TRIP + uint32_t(tid) * 4u;
+        uint32_t hm = 0;
 #pragma unroll
-        for (int i = 0; i < STREAM_PER_THREAD; ++i)
-          if (v[i] >= f.thr_s) f.offer(v[i], col0 + (i / 4) * STREAM_THREADS * 4 + (i & 3), cid);
+        for (int i = 0; i < STREAM_PER_THREAD; ++i) hm |= (v[i] >= f.thr_s ? 1u : 0u) << i;
+        while (hm) {
+          const int i = __ffs(hm) - 1;
+          hm &= hm - 1;
+          const float a0 = (i & 1) ? v[1] : v[0], a1 = (i & 1) ? v[3] : v[2], a2 = (i & 1) ? v[5] : v[4], a3 = (i & 1) ? v[7] : v[6];
+          const float b0 = (i & 2) ? a1 : a0, b1 = (i & 2) ? a3 : a2;
+          f.offer((i & 4) ? b1 : b0, col0 + uint32_t(i >> 2) * (STREAM_THREADS * 4) + uint32_t(i & 3), cid);
+        }
       }
       const bool full_buf = f.trip_barrier();    // every thread holds its scores in registers: the stage is free
       if (tid == 0 && iu < u1) issue();
