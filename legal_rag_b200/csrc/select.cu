@@ -664,7 +664,9 @@ static bool stream_plan(int nq, int64_t N, int k, StreamPlan& p) {
   const int64_t tpr = (N + STREAM_TRIP - 1) / STREAM_TRIP;
   const int64_t units = int64_t(nq) * tpr;
   if (units > (int64_t(1) << 30)) return false;
-  p.trig = std::min(4096, std::max(256, 4 * k));
+  static int trig_mult = 0;                      // candidates held before a compaction, in multiples of k (tuning knob, read once)
+  if (!trig_mult) { const char* e = getenv("LRAG_SELECT_TRIG_MULT"); trig_mult = e && atoi(e) > 0 ? atoi(e) : 4; }
+  p.trig = std::min(4096, std::max(256, trig_mult * k));
   const int per_sm = stream_smem_bytes(k, p.trig) + 3 * 1024 <= (227 * 1024) / 2 ? 2 : 1;      // CTAs that fit an SM's shared memory
   const int64_t slots = int64_t(per_sm) * sm_count();
   p.tpr = int(tpr);
