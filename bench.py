@@ -504,6 +504,9 @@ class HybridWorkload:
                 # measured in this run with the stages one after the other (setup, outside the timed region)
                 e["sms"], e["sm_share"] = share[tag], share[tag] / part["sms"]
                 e["frac_of_sm_share"] = e["frac"] / e["sm_share"]
+                e["note"] = (f"the kernel runs on {share[tag]} of {part['sms']} SMs while the other scan has the rest: `frac` divides by the WHOLE "
+                             f"GPU's peak, `frac_of_sm_share` by the kernel's share of it, `alone` is the same kernel by itself on the whole "
+                             f"GPU in this run's serial arrangement (after the power-capped dense stage)")
                 if self.alone_ms.get(tag):
                     a = work / (self.alone_ms[tag] * 1e-3) / unit_div
                     e["alone"] = {"kernel_ms": self.alone_ms[tag], "achieved": a, "frac": a / peak}
