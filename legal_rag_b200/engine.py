@@ -470,7 +470,8 @@ class HybridShard:
     tok_rows_total: int = 0
     group: object = None
     # > 0: the dense scan and the BM25 scan run side by side, the dense scan on this many SMs and BM25 on the rest
-    # (lrag_sm_reserve, csrc/partition.cu); 0: one after the other, each on the whole machine
+    # (lrag_sm_reserve, csrc/partition.cu); 0: one after the other, each on the whole machine.  The side streams and the
+    # start counter belong to the shard object: one search at a time per HybridShard (use one shard object per serving thread)
     dense_sms: int = 0
 
     def _scans_side_by_side(self, Qd, q_indptr, q_term, max_query_terms: int, kc: int):
