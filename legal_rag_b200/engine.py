@@ -501,16 +501,27 @@ class HybridShard:
             check(lib.lrag_sm_reserve(D, _ptr(self._counter), self._started, 200, _stream()), "lrag_sm_reserve")
             freed = torch.cuda.Event()
             freed.record()
+        timing = getattr(self, "_time_scans", False)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
         with torch.cuda.stream(self._side):
+            if timing:
+                ev[0].record()
             b = bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc, max_ctas=B, start_counter=self._counter)
+            if timing:
+                ev[1].record()
         main.wait_event(freed)
+        if timing:
+            ev[2].record()
         d = dense_topk(self.X, Qd, kc, self.id_base, max_ctas=D)
+        if timing:
+            ev[3].record()
+            self._scan_events = ev
         main.wait_stream(self._side)
         for t in b:
             t.record_stream(main)
         return [d, b]
 
-    def tune_partition(self, Qd, q_indptr, q_term, max_query_terms: int, Qtok=None, *, candidates=(0, 64, 68, 70, 72, 76),
+    def tune_partition(self, Qd, q_indptr, q_term, max_query_terms: int, Qtok=None, *, candidates=(0, 64, 70, 76),
                        steps: int = 3, **search_kw):
         """Times the batched step on a representative batch for several values of `dense_sms` (0 = scans one after the other)
         and keeps the fastest.  The right split depends on the workload -- how much tensor work the dense scan has against
@@ -535,8 +546,43 @@ class HybridShard:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         times = t.tolist()
-        self.dense_sms = cands[min(range(len(cands)), key=lambda i: times[i])]
-        return dict(zip(cands, times))
+        best = min(range(len(cands)), key=lambda i: times[i])
+        self.dense_sms = cands[best]
+        timed = dict(zip(cands, times))
+        if self.dense_sms > 0:
+            # refinement: the two scans' own times at the best split say where they would finish together (dense time ~ 1 / its
+            # SMs, BM25 time ~ 1 / the rest); three-step timings of neighbouring splits differ by less than their noise
+            self._time_scans = True
+            try:
+                self.search_device(Qd, q_indptr, q_term, max_query_terms, Qtok, **search_kw)
+                torch.cuda.synchronize()
+                ev = self._scan_events
+                t = torch.tensor([ev[2].elapsed_time(ev[3]), ev[0].elapsed_time(ev[1])], dtype=torch.float64, device=self.X.device)
+            finally:
+                self._time_scans = False
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            t_dense, t_bm25 = t.tolist()
+            work_d, work_b = t_dense * self.dense_sms, t_bm25 * (sms - self.dense_sms)
+            balanced = int(round(sms * work_d / (work_d + work_b) / 2.0)) * 2
+            balanced = max(8, min(sms - 8, balanced))
+            if balanced not in timed:
+                keep = self.dense_sms
+                self.dense_sms = balanced
+                self.search_device(Qd, q_indptr, q_term, max_query_terms, Qtok, **search_kw)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    self.search_device(Qd, q_indptr, q_term, max_query_terms, Qtok, **search_kw)
+                e1.record()
+                torch.cuda.synchronize()
+                tb = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=self.X.device)
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                    dist.all_reduce(tb, op=dist.ReduceOp.MAX, group=self.group)
+                timed[balanced] = float(tb.item())
+                self.dense_sms = balanced if timed[balanced] <= timed[keep] else keep
+        return timed
 
     def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
                       Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",

@@ -610,7 +610,7 @@ def test_side_by_side_scans_equal_the_serial_step(eng):
         assert torch.equal(d0[0], d1[0]) and torch.equal(d0[1], d1[1]), f"dense scan on {D} SMs changed its result"
         assert torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1]), f"BM25 scan on {2 * (148 - D)} CTAs changed its result"
     timed = shard.tune_partition(Qd, qi, qt, mx, None, candidates=(0, 68, 100, 1000), steps=1, k=k, kc=kc)
-    assert set(timed) == {0, 68, 100} and shard.dense_sms in timed and all(ms > 0 for ms in timed.values())
+    assert {0, 68, 100} <= set(timed) and 1000 not in timed and shard.dense_sms in timed and all(ms > 0 for ms in timed.values())
     s, i = shard.search_device(Qd, qi, qt, mx, None, k=k, kc=kc)
     assert torch.equal(s, ref[0]) and torch.equal(i, ref[1])
     torch.cuda.synchronize()
