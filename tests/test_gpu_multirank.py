@@ -67,11 +67,15 @@ def _hybrid_worker(rank, world, port, out_dir):
     shard = engine.HybridShard(X[lo:hi].contiguous(), host.to_device("cuda", lo, hi), T[lo:hi].contiguous(), None, id_base=lo,
                                tok_row_base=lo, tok_rows_total=N)
     s, i = shard.search_device(Q, qi, qt, mx, Qt, k=k, kc=kc)
+    shard.dense_sms = 68             # the two scans side by side on an SM partition: same sharded result
+    s2, i2 = shard.search_device(Q, qi, qt, mx, Qt, k=k, kc=kc)
+    same_side_by_side = bool(torch.equal(s, s2) and torch.equal(i, i2))
     solo = dist.new_group([0])       # collective call on every rank; the unsharded store below runs in this 1-rank group
     if rank == 0:
         full = engine.HybridShard(X, host.to_device("cuda"), T, None, id_base=0, tok_row_base=0, tok_rows_total=N, group=solo)
         fs, fi = full.search_device(Q, qi, qt, mx, Qt, k=k, kc=kc)
-        np.save(os.path.join(out_dir, "hybrid_ok.npy"), np.array([bool((fi == i).all()), bool(torch.allclose(fs, s, rtol=1e-5, atol=1e-6))]))
+        np.save(os.path.join(out_dir, "hybrid_ok.npy"), np.array([bool((fi == i).all()), bool(torch.allclose(fs, s, rtol=1e-5, atol=1e-6)),
+                                                                same_side_by_side]))
     dist.barrier()
     dist.destroy_process_group()
 
