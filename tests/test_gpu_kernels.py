@@ -680,6 +680,29 @@ def test_maxsim_scan_matches_oracle(eng, Nd, Ld, Lq, nq, k):
     check_topk_parity(s.cpu().numpy(), i.cpu().numpy(), s2.cpu().numpy(), i2.cpu().numpy(), min(k, Nd), 1e-5, what="scan-vs-gather", floor=1.0)
 
 
+def test_maxsim_scan_chunking_changes_nothing(eng, monkeypatch):
+    """The scan's work split (doc tiles per chunk, capped so that the chunks in flight stay in L2: LRAG_SCAN_L2_MB) is a
+    scheduling choice: the score matrix is bit-identical for tiny, default and unlimited chunks, on a store large enough
+    for the cap to bind, and a sample of it matches the oracle."""
+    rng = np.random.default_rng(8)
+    Nd, Ld, Lq, nq = 12_000, 128, 32, 64
+    Dd, Dr = _bf16(_unit(rng, (Nd, Ld, 128)))
+    Qd, Qr = _bf16(_unit(rng, (nq, Lq, 128)))
+    doclen = rng.integers(1, Ld + 1, Nd).astype(np.int32)
+    dl = torch.from_numpy(doclen).cuda()
+    outs = []
+    for mb in ("0", None, "4096"):
+        if mb is None:
+            monkeypatch.delenv("LRAG_SCAN_L2_MB", raising=False)
+        else:
+            monkeypatch.setenv("LRAG_SCAN_L2_MB", mb)
+        outs.append(eng.maxsim_scan_scores(Dd, dl, Qd))
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    rows = rng.choice(Nd, 300, replace=False).astype(np.int64)
+    want = omaxsim.maxsim_scores(Qr[:3], Dr, doclen, np.tile(rows, (3, 1)))
+    np.testing.assert_allclose(outs[1][:3].cpu().numpy()[:, rows], want, rtol=2e-4, atol=2e-4)
+
+
 def test_maxsim_scan_rejects_row_lengths_that_do_not_tile(eng):
     D = torch.zeros((10, 96, 128), dtype=torch.bfloat16, device="cuda")
     Q = torch.zeros((2, 32, 128), dtype=torch.bfloat16, device="cuda")
