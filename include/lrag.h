@@ -176,14 +176,14 @@ int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id, const flo
                          const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
                          int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, float* out_score,
                          int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream);
-/* The same with a grid of at most `max_ctas` CTAs (0 = two per SM over the whole machine) whose CTAs add one to
- * *start_counter (may be NULL) as they become resident: the BM25 side of an SM partition (lrag_sm_reserve).
- * lrag_bm25_grid tells how many CTAs such a call launches.  Results do not depend on max_ctas. */
-int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_ctas);
+/* The same confined to `max_sms` SMs (0 = the whole machine; the scan keeps as many CTAs resident per SM as fit, two)
+ * whose CTAs add one to *start_counter (may be NULL) as they become resident: the BM25 side of an SM partition
+ * (lrag_sm_reserve).  lrag_bm25_grid tells how many CTAs such a call launches.  Results do not depend on max_sms. */
+int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_sms);
 int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
                         const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
                         const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
-                        int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_ctas,
+                        int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_sms,
                         unsigned long long* start_counter, float* out_score, int64_t* out_id, void* ws,
                         size_t ws_bytes, lrag_stream_t stream);
 
@@ -192,7 +192,7 @@ int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id, const floa
  * channels one after the other on the CPU, legalrag/retrieval/hybrid_retriever.py:295-299).  The dense scan
  * (192 KB of shared memory per CTA) and the BM25 scan (2 x 113 KB per SM) cannot share an SM.  lrag_sm_reserve parks
  * one CTA holding 200 KB of shared memory on `ctas` SMs until *counter >= target (or `timeout_ms` passes): launch
- * it first, then lrag_bm25_topk_part on a second stream with max_ctas = 2 x (SMs - ctas) and the same counter
+ * it first, then lrag_bm25_topk_part on a second stream with max_sms = SMs - ctas and the same counter
  * (target = counter value before + lrag_bm25_grid(...)); its CTAs can only land on the other SMs.  A third stream
  * that waits for the reservation then runs lrag_dense_topk_bf16_part with max_ctas = ctas on exactly the SMs the
  * reservation gives back.  On a power-capped board the two stages side by side draw a steady load at one clock;

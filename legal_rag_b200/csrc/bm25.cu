@@ -1211,27 +1211,27 @@ extern "C" int lrag_bm25_topk_dense(const int64_t* indptr, const int32_t* doc_id
                              max_query_terms, N, k, id_base, nonneg, impact_bound, 0, nullptr, out_score, out_id, ws, ws_bytes, stream_);
 }
 
-// CTAs the scan launches when it may use at most `max_ctas` (0 = the whole machine)
-static unsigned long long bm25_grid(const Bm25Plan& pl, int max_ctas, int occ) {
-  unsigned long long grid = (unsigned long long)occ * sm_count();
-  if (max_ctas > 0 && (unsigned long long)max_ctas < grid) grid = max_ctas;
+// CTAs the scan launches when it may use at most `max_sms` SMs (0 = the whole machine): `occ` resident CTAs on each
+static unsigned long long bm25_grid(const Bm25Plan& pl, int max_sms, int occ) {
+  const int sms = max_sms > 0 && max_sms < sm_count() ? max_sms : sm_count();
+  unsigned long long grid = (unsigned long long)occ * sms;
   if (grid > pl.total_items) grid = pl.total_items;
   return grid;
 }
 
-extern "C" int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_ctas) {
-  if (N < 0 || nq <= 0 || k <= 0 || k > LRAG_MAX_K || max_ctas < 0 || !initialised()) return 0;
+extern "C" int lrag_bm25_grid(int64_t N, int nq, int k, int64_t max_query_terms, int max_sms) {
+  if (N < 0 || nq <= 0 || k <= 0 || k > LRAG_MAX_K || max_sms < 0 || !initialised()) return 0;
   const Bm25Plan pl = bm25_plan(N, nq, k, max_query_terms, sm_count());
   int occ = 0;
   cudaFuncSetAttribute(bm25_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(pl.smem));
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem) != cudaSuccess || occ < 1) return 0;
-  return int(bm25_grid(pl, max_ctas, occ));
+  return int(bm25_grid(pl, max_sms, occ));
 }
 
 extern "C" int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id, const float* impact, int64_t V, int64_t nnz,
                                    const int32_t* dense_term, const float* dense_rows, int n_dense, int64_t dense_stride,
                                    const int64_t* q_indptr, const int32_t* q_term, int nq, int64_t max_query_terms,
-                                   int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_ctas,
+                                   int64_t N, int k, int64_t id_base, int nonneg, float impact_bound, int max_sms,
                                    unsigned long long* start_counter, float* out_score,
                                    int64_t* out_id, void* ws, size_t ws_bytes, lrag_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1275,7 +1275,7 @@ extern "C" int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id,
   p.ws.q_inv_scale = reinterpret_cast<float*>(w + pl.off[12]);
   p.impact_bound = impact_bound;
   p.start_counter = start_counter;
-  LRAG_REQUIRE(max_ctas >= 0, "bm25_topk: max_ctas=%d must be >= 0 (0 = the whole machine)", max_ctas);
+  LRAG_REQUIRE(max_sms >= 0, "bm25_topk: max_sms=%d must be >= 0 (0 = the whole machine)", max_sms);
 
   static size_t smem_set[LRAG_MAX_DEVICES] = {};      // function attributes are per device
   const int dev = device_slot();
@@ -1286,7 +1286,7 @@ extern "C" int lrag_bm25_topk_part(const int64_t* indptr, const int32_t* doc_id,
   int occ = 0;
   LRAG_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bm25_scan_kernel, BM25_THREADS, pl.smem));
   LRAG_REQUIRE(occ >= 1, "bm25_topk: the scan kernel does not fit on an SM (smem %zu)", pl.smem);
-  const unsigned long long grid = bm25_grid(pl, max_ctas, occ);
+  const unsigned long long grid = bm25_grid(pl, max_sms, occ);
   const int prep_blocks = int(std::min<int64_t>((int64_t(nq) + 7) / 8, 4 * int64_t(sms)));
   bm25_prepare_kernel<<<prep_blocks, 256, 0, stream>>>(p);
   LRAG_CHECK_CUDA(cudaGetLastError()); note_launch();

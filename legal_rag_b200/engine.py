@@ -206,9 +206,9 @@ def bm25_set_item_slabs(slabs: int) -> None:
 
 
 def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int, k: int, *,
-              max_ctas: int = 0, start_counter: Optional[torch.Tensor] = None):
-    """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV).  max_ctas > 0 limits the scan's
-    grid and start_counter (int64 [1]) is incremented by every CTA as it starts (HybridShard's side-by-side scans);
+              max_sms: int = 0, start_counter: Optional[torch.Tensor] = None):
+    """q_indptr [nq + 1] int64, q_term [*] int32 term ids (repeats allowed, -1 = OOV).  max_sms > 0 confines the scan to that
+    many SMs and start_counter (int64 [1]) is incremented by every CTA as it starts (HybridShard's side-by-side scans);
     the result depends on neither."""
     lib = _native.init(index.indptr.device.index)
     dev = index.indptr.device
@@ -226,7 +226,7 @@ def bm25_topk(index: Bm25DeviceIndex, q_indptr: torch.Tensor, q_term: torch.Tens
                                  _ptr(index.dense_term) if n_dense else None, _ptr(index.dense_rows) if n_dense else None, n_dense,
                                  int(index.dense_rows.shape[1]) if n_dense else 0, _ptr(q_indptr),
                                  _ptr(q_term), nq, max_query_terms, index.n_docs, k, index.id_base, 1 if index.nonneg else 0,
-                                 index.impact_bound, int(max_ctas), _ptr(start_counter), _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
+                                 index.impact_bound, int(max_sms), _ptr(start_counter), _ptr(s), _ptr(i), _ptr(ws), ws.numel(), _stream())
     check(rc, "lrag_bm25_topk")
     return s, i
 
@@ -490,9 +490,8 @@ class HybridShard:
             self._started = 0
         sms = int(lib.lrag_sm_count())
         D = max(1, min(int(self.dense_sms), sms - 1))
-        B = 2 * (sms - D)
         nq = q_indptr.numel() - 1
-        self._started += int(lib.lrag_bm25_grid(self.bm25.n_docs, nq, kc, max_query_terms, B))
+        self._started += int(lib.lrag_bm25_grid(self.bm25.n_docs, nq, kc, max_query_terms, sms - D))
         if not self.bm25._dense_built:
             self.bm25.build_dense_rows()
         self._side.wait_stream(main)
@@ -506,7 +505,7 @@ class HybridShard:
         with torch.cuda.stream(self._side):
             if timing:
                 ev[0].record()
-            b = bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc, max_ctas=B, start_counter=self._counter)
+            b = bm25_topk(self.bm25, q_indptr, q_term, max_query_terms, kc, max_sms=sms - D, start_counter=self._counter)
             if timing:
                 ev[1].record()
         main.wait_event(freed)

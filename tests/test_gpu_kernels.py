@@ -606,9 +606,9 @@ def test_side_by_side_scans_equal_the_serial_step(eng):
             s, i = shard.search_device(Qd, qi, qt, mx, None, k=k, kc=kc)
             assert torch.equal(s, ref[0]) and torch.equal(i, ref[1]), f"dense on {D} SMs changed the fused result"
         d1 = eng.dense_topk(Xd, Qd, kc, max_ctas=D)
-        b1 = eng.bm25_topk(index, qi, qt, mx, kc, max_ctas=2 * (148 - D))
+        b1 = eng.bm25_topk(index, qi, qt, mx, kc, max_sms=148 - D)
         assert torch.equal(d0[0], d1[0]) and torch.equal(d0[1], d1[1]), f"dense scan on {D} SMs changed its result"
-        assert torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1]), f"BM25 scan on {2 * (148 - D)} CTAs changed its result"
+        assert torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1]), f"BM25 scan on {148 - D} SMs changed its result"
     timed = shard.tune_partition(Qd, qi, qt, mx, None, candidates=(0, 68, 100, 1000), steps=1, k=k, kc=kc)
     assert {0, 68, 100} <= set(timed) and 1000 not in timed and shard.dense_sms in timed and all(ms > 0 for ms in timed.values())
     s, i = shard.search_device(Qd, qi, qt, mx, None, k=k, kc=kc)
