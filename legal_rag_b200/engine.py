@@ -5,6 +5,7 @@ the C ABI.  Every function takes CUDA tensors, enqueues on the current torch str
 """
 from __future__ import annotations
 
+import threading
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
 
@@ -646,6 +647,8 @@ class GraphedHybridQuery:
                  breakdown: bool = False, **fuse_kw):
         """k: hits returned; kc: per-channel list length (default k); breakdown: also return the fusion breakdown [nq, k, 8]
         and the two channels' id lists (what HybridRetriever.search needs to rebuild the reference's score_breakdown)."""
+        # static input / output buffers: one search at a time per captured graph (callers on several host threads take it)
+        self.lock = threading.Lock()
         self.X = _need(X, torch.bfloat16, 2, "X")
         self.bm25, self.nq, self.max_terms = bm25, int(nq), int(max_terms)
         self.kc = min(int(kc if kc is not None else k), int(X.shape[0]), LRAG_MAX_K)
@@ -687,7 +690,8 @@ class GraphedHybridQuery:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: another host thread's CUDA calls (a search on a different graph) must not abort this capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             fused, self.out_di, self.out_bi = run()
             self.out_s, self.out_i = fused[0], fused[1]
             self.out_bd = fused[2] if self.breakdown else None

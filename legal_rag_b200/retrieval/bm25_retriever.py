@@ -7,6 +7,7 @@ import logging
 from pathlib import Path
 from typing import Callable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from .. import engine
@@ -54,15 +55,26 @@ class BM25Retriever:
         self.load()
         host, dev = self.host_index, self.device_index
         k = max(1, min(int(top_k), engine.LRAG_MAX_K))
-        token_lists = [list(t) for t in token_lists]
-        longest = max((len(t) for t in token_lists), default=0)
-        if longest > engine.LRAG_BM25_MAX_QUERY_TERMS:
+        qi, qt, _ = host.encode_queries([list(t) for t in token_lists])
+        # tokens outside the vocabulary score nothing (rank_bm25: `self.doc_freqs[...].get(q) or 0`), so they do not take up
+        # slots of the kernel's per-query term table (jieba emits whitespace and punctuation as tokens of their own)
+        known = qt >= 0
+        seen = np.concatenate([[0], np.cumsum(known)]).astype(np.int64)
+        lens = seen[qi[1:]] - seen[qi[:-1]]
+        qt = qt[known]
+        qi = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        mx = int(lens.max()) if lens.size else 0
+        if mx > engine.LRAG_BM25_MAX_QUERY_TERMS:
             # rank_bm25 scores every token (bm25_retriever.py:74); the kernel's per-query term table holds 128
             logging.getLogger("legal_rag_b200.retrieval").warning(
-                "[BM25] a query of %d tokens is scored on its first %d (kernel limit LRAG_BM25_MAX_QUERY_TERMS); the reference "
-                "would score all of them", longest, engine.LRAG_BM25_MAX_QUERY_TERMS)
-            token_lists = [t[: engine.LRAG_BM25_MAX_QUERY_TERMS] for t in token_lists]
-        qi, qt, mx = host.encode_queries(token_lists)
+                "[BM25] a query of %d in-vocabulary tokens is scored on its first %d (kernel limit LRAG_BM25_MAX_QUERY_TERMS); "
+                "the reference would score all of them", mx, engine.LRAG_BM25_MAX_QUERY_TERMS)
+            cap = engine.LRAG_BM25_MAX_QUERY_TERMS
+            keep = np.concatenate([np.arange(a, min(b, a + cap)) for a, b in zip(qi[:-1], qi[1:])]).astype(np.int64)
+            qt = qt[keep]
+            lens = np.minimum(lens, cap)
+            qi = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+            mx = cap
         return engine.bm25_topk(dev, torch.from_numpy(qi).to(self.device), torch.from_numpy(qt).to(self.device), mx, k)
 
     def search(self, query: str, top_k: int) -> List[Tuple[LawChunk, float]]:

@@ -4,6 +4,8 @@ decision)` keeps the reference's positional order; `search_batch` is the through
 queries through every channel in one kernel launch each, fused on the device)."""
 from __future__ import annotations
 
+import threading
+
 import logging
 import time
 import traceback
@@ -106,6 +108,7 @@ class HybridRetriever:
         self._align_key = None   # (store / index mtimes) the alignment verdict below was computed for
         self._aligned = False
         self._graphs: Dict[Any, Any] = {}     # captured single-query pipelines, by (depth, top_k, fusion knobs, store snapshot)
+        self._graphs_lock = threading.Lock()
         self.fast_path_used = False
         self.graph = None        # plug a retrieval.GraphRetriever(cfg, graph=<graph store with walk()>) in here: the graph
                                  # store is host-side and injected, its scoring stage runs on the GPU
@@ -288,6 +291,15 @@ class HybridRetriever:
             self._graphs.clear()                  # captured pipelines hold the old snapshot's device tensors
         return self._aligned
 
+    def _capture_graph(self, key, store, bm, top_k, depth, max_terms, knobs, floor):
+        if len(self._graphs) >= 32:
+            self._graphs.pop(next(iter(self._graphs)))
+        g = self._graphs[key] = engine.GraphedHybridQuery(
+            store.index.matrix, bm.device_index, k=top_k, kc=depth, nq=1, max_terms=max_terms, breakdown=True,
+            method=knobs["method"], w_dense=knobs["w_dense"], w_bm25=knobs["w_bm25"], w_colbert=knobs["w_colbert"],
+            rrf_k=knobs["rrf_k"], alpha=knobs["alpha"], min_final=floor)
+        return g
+
     def _search_graphed(self, question: str, top_k: int, depth: int, decision: Any, laps: "_Laps") -> Optional[List[RetrievalHit]]:
         """search() for the common online case -- dense + BM25 channels over row-aligned stores, no ColBERT channel, no graph
         expansion asked for, no reranker -- as ONE captured CUDA graph per query (engine.GraphedHybridQuery: both scans on
@@ -309,23 +321,23 @@ class HybridRetriever:
         knobs = self._fusion_knobs()
         floor = float(getattr(rcfg, "min_final_score", 0.0))
         key = (depth, top_k, tuple(sorted(knobs.items())), floor, id(store.index), id(bm.device_index))
-        g = self._graphs.get(key)
-        if g is None:
-            if len(self._graphs) >= 32:
-                self._graphs.pop(next(iter(self._graphs)))
-            g = self._graphs[key] = engine.GraphedHybridQuery(
-                store.index.matrix, bm.device_index, k=top_k, kc=depth, nq=1, max_terms=max_terms, breakdown=True,
-                method=knobs["method"], w_dense=knobs["w_dense"], w_bm25=knobs["w_bm25"], w_colbert=knobs["w_colbert"],
-                rrf_k=knobs["rrf_k"], alpha=knobs["alpha"], min_final=floor)
+        with self._graphs_lock:               # one thread captures a pipeline, the others wait for it
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._capture_graph(key, store, bm, top_k, depth, max_terms, knobs, floor)
         q_vec = torch.from_numpy(store._embed([question], is_query=True))
         _, qt, _ = bm.host_index.encode_queries([tokens])
-        fs, fi = g.search(q_vec, [qt.tolist()])
+        # the captured graph works on static buffers: searches from several host threads (Starlette's thread pool)
+        # take turns on it, and everything this call needs is copied out before the next one may start
+        with g.lock:
+            fs, fi = g.search(q_vec, [qt.tolist()])
+            scores, rows, parts = fs[0].tolist(), fi[0].tolist(), g._h_bd[0].tolist()
+            in_dense, in_bm25 = set(g._h_di[0].tolist()), set(g._h_bi[0].tolist())
         laps.mark("dense"); laps.mark("bm25"); laps.mark("colbert"); laps.mark("fuse")
-        in_dense, in_bm25 = set(g._h_di[0].tolist()), set(g._h_bi[0].tolist())
         weights = {"dense": knobs["w_dense"], "bm25": knobs["w_bm25"], "colbert": knobs["w_colbert"]}
         chunks = store.chunks
         out: List[RetrievalHit] = []
-        for r, (score, j, b) in enumerate(zip(fs[0].tolist(), fi[0].tolist(), g._h_bd[0].tolist()), start=1):
+        for r, (score, j, b) in enumerate(zip(scores, rows, parts), start=1):
             if j < 0:
                 break
             contrib = {"dense": b[5], "bm25": b[6], "colbert": b[7]}

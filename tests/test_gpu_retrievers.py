@@ -177,6 +177,61 @@ def test_search_fast_path_equals_general_path(world, method):
             assert all(x.score >= y.score for x, y in zip(a, a[1:]))
 
 
+def test_search_fast_path_from_several_host_threads(world):
+    """the reference's API calls HybridRetriever.search from Starlette's worker threads.  The captured pipeline
+    works on static buffers, so concurrent callers take turns on it (GraphedHybridQuery.lock) and the first one captures it
+    while the others wait; every thread must get the single-threaded answer."""
+    import copy
+    import threading
+    from legal_rag_b200.retrieval import HybridRetriever
+    cfg = copy.deepcopy(world["cfg"])
+    cfg.retrieval.enable_colbert = False
+    hr, ref = HybridRetriever(cfg), HybridRetriever(cfg)
+    want = {qn: [(h.chunk.id, h.score) for h in ref.search(qn, None, 10)] for qn in QUESTIONS}
+    assert ref.fast_path_used
+    errors = []
+
+    def worker(seed):
+        try:
+            for it in range(25):
+                qn = QUESTIONS[(seed + it) % len(QUESTIONS)]
+                got = [(h.chunk.id, h.score) for h in hr.search(qn, None, 10)]
+                if got != want[qn]:
+                    errors.append(f"thread {seed} iteration {it}: {got[:3]} != {want[qn][:3]}")
+                    return
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {seed}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert hr.fast_path_used and len(hr._graphs) == 1
+
+
+def test_bm25_long_question_with_unknown_tokens_is_scored_whole(world):
+    """rank_bm25's get_scores has no token limit (bm25_retriever.py:74); the kernel's term table holds 128 IN-VOCABULARY
+    tokens.  Out-of-vocabulary tokens (jieba's whitespace / punctuation tokens, mostly) score nothing and must not use up
+    that budget: a 300-token question with 60 known tokens ranks exactly like its known tokens alone."""
+    from legal_rag_b200.retrieval import BM25Retriever
+    bm = BM25Retriever(world["cfg"], tokenizer=lambda q: q.split(" "))
+    known = (QUESTIONS[0] + " " + QUESTIONS[1] + " " + QUESTIONS[3]).lower().replace("?", "").split(" ")
+    known = (known * 3)[:60]
+    rng = np.random.default_rng(5)
+    noisy = []
+    for w in known:
+        noisy.extend([" ", "\u3000", f"zzqx{rng.integers(1 << 30)}", "?"])
+        noisy.append(w)
+    assert len(noisy) == 300
+    s0, i0 = bm.search_ids([known], 50)
+    s1, i1 = bm.search_ids([noisy, [], ["zzqx-only-unknown"], known], 50)
+    assert torch.equal(s0[0], s1[0]) and torch.equal(i0[0], i1[0])
+    assert torch.equal(s0[0], s1[3]) and torch.equal(i0[0], i1[3])
+    assert float(s1[1].abs().max()) == 0.0 and float(s1[2].abs().max()) == 0.0     # the reference ranks all-zero scores too
+
+
 def test_incremental_add_is_searchable_and_persisted(world):
     from legal_rag_b200.retrieval import VectorStore, artifacts, builders
     from legal_rag_b200.schemas import LawChunk
