@@ -969,6 +969,14 @@ def measure_native(wl, steps, warmup, rank, world, local_rank, device, peaks, e2
             "global_queries_per_s": wl.nq * steps / (ms * 1e-3),
             "kernel_ms_per_step": by_tag,
             "rest_of_step_ms": ms / steps - (wl.critical_kernel_ms(by_tag) if hasattr(wl, "critical_kernel_ms") else sum(by_tag.values()))}
+    if roof.get("stages"):
+        # the step as a whole against its stages' rooflines: the time a machine that ran every stage alone at the measured
+        # peak bounding it would need for one step, over the measured step.  With the two scans side by side neither kernel's
+        # own `frac` (against the WHOLE GPU's peak) can approach 1 -- they share the machine -- but their sum can.
+        ideal = {st["kernel"]: st["kernel_ms"] * st["frac"] for st in roof["stages"]}
+        roof["step"] = {"ideal_ms": sum(ideal.values()), "ideal_ms_by_stage": ideal, "ms_per_step": ms / steps,
+                        "frac": sum(ideal.values()) / (ms / steps),
+                        "what": "sum over stages of (algorithmic work / the measured peak that bounds the stage) / measured step time"}
     if e2e:
         h2d, d2h = wl.e2e_bytes()
         line["e2e"] = {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

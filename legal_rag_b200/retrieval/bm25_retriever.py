@@ -4,6 +4,7 @@ liblrag BM25 kernel -- scoring and the full ranking the reference does in Python
 from __future__ import annotations
 
 import logging
+import threading
 from pathlib import Path
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -23,6 +24,7 @@ class BM25Retriever:
         self.device = torch.device(getattr(cfg, "device", None) or "cuda")
         self.tokenizer = tokenizer or encoders.default_query_tokenizer()
         self._loaded = False
+        self._load_lock = threading.Lock()
         self._bm25_mtime: Optional[float] = None
         self.bm25 = None                          # the unpickled BM25Okapi (or its stand-in)
         self.chunks: List[LawChunk] = []
@@ -36,6 +38,11 @@ class BM25Retriever:
         current_mtime = self.bm25_path.stat().st_mtime
         if self._loaded and self._bm25_mtime == current_mtime:
             return
+        with self._load_lock:                    # threads that arrive together load once and share the snapshot
+            if not (self._loaded and self._bm25_mtime == current_mtime):
+                self._load_locked(current_mtime)
+
+    def _load_locked(self, current_mtime: float) -> None:
         obj = artifacts.read_bm25_pickle(self.bm25_path)
         bm25 = obj.get("bm25")
         if bm25 is None:

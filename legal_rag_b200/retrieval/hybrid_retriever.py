@@ -281,7 +281,11 @@ class HybridRetriever:
         self.bm25.load()
         key = (self.dense.store._index_mtime, self.dense.store._meta_mtime, self.bm25._bm25_mtime,
                None if self.colbert is None else self.colbert._meta_mtime)
-        if key != self._align_key:
+        if key == self._align_key:
+            return self._aligned
+        with self._graphs_lock:                   # one thread checks a new snapshot, the others wait for its verdict
+            if key == self._align_key:
+                return self._aligned
             chunks = self.dense.store.chunks
             ok = len(chunks) == len(self.bm25.chunks) and all(a.id == b.id for a, b in zip(chunks, self.bm25.chunks))
             if ok and self.colbert is not None:

@@ -128,6 +128,9 @@ class VectorStore:
         if self.index is not None and self.chunks and self._index_mtime == index_mtime and self._meta_mtime == meta_mtime:
             return
         with self._load_lock:
+            # threads that arrived together (Starlette's pool on a cold start) load once and share the snapshot
+            if self.index is not None and self.chunks and self._index_mtime == index_mtime and self._meta_mtime == meta_mtime:
+                return
             X, info = artifacts.read_faiss_index(self.index_path)
             if info.get("metric", artifacts.METRIC_INNER_PRODUCT) != artifacts.METRIC_INNER_PRODUCT:
                 # the reference builds inner-product indexes only (builders/faiss_builder.py:84); scanning an L2 index as
