@@ -54,6 +54,128 @@ struct ScanParams {
   int debug;           // timing experiments: 1 = epilogue reads nothing (accumulators handed straight back)
 };
 
+// 32 accumulator words -> their maximum (and m) through three-input maxima (FMNMX3): 16 instructions in 4 dependent levels
+__device__ __forceinline__ float scan_max32(const uint32_t (&vv)[32], float m) {
+  float l1[11];
+#pragma unroll
+  for (int g = 0; g < 10; ++g)
+    l1[g] = fmaxf(fmaxf(__uint_as_float(vv[3 * g]), __uint_as_float(vv[3 * g + 1])), __uint_as_float(vv[3 * g + 2]));
+  l1[10] = fmaxf(__uint_as_float(vv[30]), __uint_as_float(vv[31]));
+  const float a0 = fmaxf(fmaxf(l1[0], l1[1]), l1[2]), a1 = fmaxf(fmaxf(l1[3], l1[4]), l1[5]);
+  const float a2 = fmaxf(fmaxf(l1[6], l1[7]), l1[8]), a3 = fmaxf(fmaxf(l1[9], l1[10]), m);
+  return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+}
+
+// Epilogue of one warp: SC_EPQ warps per TMEM lane quadrant (= query inside the block); warp `slot` of a quadrant takes columns
+// [slot * SC_WCOLS, (slot + 1) * SC_WCOLS) of every tile.  A document longer than that (LD = 256) spans two warps: their partial
+// maxima meet in shared memory and the warp that holds the document's last columns finishes it.  LD (32, 64, 128 or 256) and
+// HAS_DL (per-document lengths given: tokens past a document's length are masked) are compile-time: a warp executes ~110
+// instructions per tile in the unmasked LD = 128 instance against ~290 with run-time column maps and mask tests, and the
+// epilogue of a tile is one warp's dependent instruction stream (tools/micro/tmem_ld.cu: TMEM read-back itself delivers
+// 730-940 B/clk/SM, 6-7x what is needed).
+template <int LD, bool HAS_DL>
+__device__ __forceinline__ void scan_epilogue(const ScanParams& p, uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                              float* part, int quad, int slot, int lane) {
+  constexpr int DPT = SC_BN / LD;                              // documents per tile
+  constexpr int SPAN = LD > SC_WCOLS ? LD / SC_WCOLS : 1;      // warps that share one document
+  static_assert(SPAN <= 2 || SC_EPQ > 2, "partial hand-over below assumes the finisher reads its predecessors' slots");
+  const int quad_bar = quad + 1;                               // named barrier of the quadrant's warps
+  const int c0 = slot * SC_WCHUNKS;
+  uint32_t it = 0;
+  if (p.debug == 1) {
+    // timing experiment (LRAG_SCAN_DEBUG=1): the mainloop alone, accumulators handed straight back
+    for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+      const int64_t dt0 = (u / p.QB) * p.chunk_tiles, dt1 = min(p.DT, dt0 + p.chunk_tiles);
+      for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
+        mbar_wait(&tfull_bar[it & 1], (it >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[it & 1]);
+      }
+    }
+    return;
+  }
+  for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
+    const int qb = int(u % p.QB);
+    const int64_t dt0 = (u / p.QB) * p.chunk_tiles;
+    const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
+    const int q = qb * 4 + quad;
+    float* out_row = p.out + size_t(q < p.nq ? q : 0) * p.ld_out;
+    for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
+      const int64_t doc0 = dt * DPT;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      // document lengths of the tile, fetched before the accumulator is waited for
+      int dl_mine = 0;
+      if (HAS_DL && lane < DPT) {
+        const int64_t doc = doc0 + lane;
+        dl_mine = doc < p.Nd ? min(p.doclen[doc], LD) : 0;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
+      float m = SC_PAD_FILL;
+      // the next chunk's TMEM load is in flight while this one is reduced.  (Requesting all of a warp's columns at once and
+      // waiting once was measured: 86.5 ms against 67.1 ms for 64 queries x 1M documents.)
+      uint32_t v[2][32];
+      // chunk i of this warp: columns (c0 + i) * 32 ...: document `din` of the tile, its tokens off .. off + 31
+      auto din_of = [&](int i) { return ((c0 + i) * 32) / LD; };
+      auto off_of = [&](int i) { return LD > SC_WCOLS ? ((c0 + i) * 32) % LD : (i * 32) % LD; };   // LD <= SC_WCOLS: the same for both slots
+      int dl_c[SC_WCHUNKS];
+#pragma unroll
+      for (int i = 0; i < SC_WCHUNKS; ++i)
+        dl_c[i] = HAS_DL ? __shfl_sync(0xffffffffu, dl_mine, din_of(i)) : LD;
+      if (off_of(0) < dl_c[0]) tmem_ld_32x32(taddr + c0 * 32, v[0]);
+#pragma unroll
+      for (int i = 0; i < SC_WCHUNKS; ++i) {
+        const int c = c0 + i;
+        const int off = off_of(i), dl = dl_c[i];
+        const bool live = off < dl;                                             // warp-uniform: the chunk holds unmasked tokens
+        tmem_ld_wait();
+        if (i + 1 < SC_WCHUNKS) {
+          const int j = i + 1 < SC_WCHUNKS ? i + 1 : i;
+          if (off_of(j) < dl_c[j]) tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
+        }
+        if (live) {
+          const uint32_t (&vv)[32] = v[i & 1];
+          if (!HAS_DL || off + 32 <= dl) {
+            m = scan_max32(vv, m);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (off + j < dl) m = fmaxf(m, __uint_as_float(vv[j]));
+          }
+        }
+        const bool doc_ends = off + 32 == LD;                                     // the document's last columns are in this chunk
+        const bool mine_ends = i == SC_WCHUNKS - 1 && !doc_ends && SPAN > 1;       // my columns end inside a longer document
+        if (mine_ends) {
+          // One partial slot per warp (shared memory is full: 227 KB of tiles).  The previous tile's partial is read by its
+          // finisher before that warp hands the previous accumulator back, so "every epilogue warp has drained the previous
+          // tile" (the accumulator's empty barrier) is what makes the slot free.
+          if (it > 0) mbar_wait(&tempty_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+          part[(quad * (SC_EPQ - 1) + slot) * 32 + lane] = m;                           // handed to the warp that finishes the document
+        } else if (doc_ends) {
+          if (SPAN > 1) {
+            asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");   // the partners' partial maxima are in smem
+            for (int s2 = slot - SPAN + 1; s2 < slot; ++s2) m = fmaxf(m, part[(quad * (SC_EPQ - 1) + s2) * 32 + lane]);
+          }
+          float sum = (lane < p.Lq) ? m : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const int64_t doc = doc0 + din_of(i);
+          if (lane == 0 && q < p.nq && doc < p.Nd) out_row[doc] = sum;
+          m = SC_PAD_FILL;
+        }
+      }
+      // a warp that only handed a partial over still meets the quadrant's barrier (once per tile, every warp)
+      if (SPAN > 1 && (slot % SPAN) != SPAN - 1) asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+}
+
 // Work split: the doc tiles are cut into chunks; unit u = (chunk u / QB, query block u % QB) goes to CTA u mod grid.
 // A unit's query block sits in shared memory (the A operand of every tile of the unit), only doc tiles stream.
 // The QB units of a chunk are consecutive, so they run on neighbouring CTAs at the same time: a doc tile comes from
@@ -167,98 +289,21 @@ maxsim_scan_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // cost is the dependent max chains, which is why it is spread over 16 warps (4 per scheduler).
     const int quad = warp & 3;
     const int slot = (warp - 2) >> 2;
-    const int dpt = SC_BN / p.Ld;                  // documents per tile
-    const int span = p.Ld > SC_WCOLS ? p.Ld / SC_WCOLS : 1;      // warps that share one document
-    const int quad_bar = quad + 1;                 // named barrier of the quadrant's warps
-    // which document of the tile, and which of its tokens, each of this warp's 32-column chunks holds: the same for every
-    // tile (Ld is a power of two: 32, 64, 128 or 256)
-    const int c0 = slot * SC_WCHUNKS;
-    const int ld_shift = 31 - __clz(p.Ld);
-    int off_c[SC_WCHUNKS], din_c[SC_WCHUNKS];
-#pragma unroll
-    for (int i = 0; i < SC_WCHUNKS; ++i) {
-      const int col = (c0 + i) * 32;
-      din_c[i] = col >> ld_shift;
-      off_c[i] = col & (p.Ld - 1);
-    }
-    uint32_t it = 0;
-    for (int64_t u = blockIdx.x; u < p.units; u += gridDim.x) {
-      const int qb = int(u % p.QB);
-      const int64_t dt0 = (u / p.QB) * p.chunk_tiles;
-      const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
-      const int q = qb * 4 + quad;
-      for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
-        const int64_t doc0 = dt * dpt;
-        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        // document lengths of the tile, fetched before the accumulator is waited for
-        int dl_mine = 0;
-        if (lane < dpt) {
-          const int64_t doc = doc0 + lane;
-          dl_mine = doc < p.Nd ? (p.doclen ? min(p.doclen[doc], p.Ld) : p.Ld) : 0;
-        }
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
-        float m = SC_PAD_FILL;
-        // the next chunk's TMEM load is in flight while this one is reduced.  (Requesting all of a warp's columns at once and
-        // waiting once was measured: 86.5 ms against 67.1 ms for 64 queries x 1M documents -- 128 live registers of loaded
-        // values cost more than the overlap gains.)
-        uint32_t v[2][32];
-        int dl_c[SC_WCHUNKS];
-#pragma unroll
-        for (int i = 0; i < SC_WCHUNKS; ++i) dl_c[i] = p.debug == 1 ? 0 : __shfl_sync(0xffffffffu, dl_mine, din_c[i]);
-        if (off_c[0] < dl_c[0]) tmem_ld_32x32(taddr + c0 * 32, v[0]);
-#pragma unroll
-        for (int i = 0; i < SC_WCHUNKS; ++i) {
-          const int c = c0 + i;
-          const int din = din_c[i], off = off_c[i], dl = dl_c[i];
-          tmem_ld_wait();
-          if (i + 1 < SC_WCHUNKS && off_c[i + 1 < SC_WCHUNKS ? i + 1 : i] < dl_c[i + 1 < SC_WCHUNKS ? i + 1 : i])
-            tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
-          if (off < dl) {                            // warp-uniform: the chunk holds unmasked tokens
-            const uint32_t* vv = v[i & 1];
-            if (off + 32 <= dl) {
-              // 32 values -> 1 through three-input maxima (FMNMX3): 16 instructions in 4 dependent levels
-              float l1[11];
-#pragma unroll
-              for (int g = 0; g < 10; ++g)
-                l1[g] = fmaxf(fmaxf(__uint_as_float(vv[3 * g]), __uint_as_float(vv[3 * g + 1])), __uint_as_float(vv[3 * g + 2]));
-              l1[10] = fmaxf(__uint_as_float(vv[30]), __uint_as_float(vv[31]));
-              const float a0 = fmaxf(fmaxf(l1[0], l1[1]), l1[2]), a1 = fmaxf(fmaxf(l1[3], l1[4]), l1[5]);
-              const float a2 = fmaxf(fmaxf(l1[6], l1[7]), l1[8]), a3 = fmaxf(fmaxf(l1[9], l1[10]), m);
-              m = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (off + j < dl) m = fmaxf(m, __uint_as_float(vv[j]));
-            }
-          }
-          const bool doc_ends = off + 32 == p.Ld;                                   // the document's last columns are in this chunk
-          const bool mine_ends = i == SC_WCHUNKS - 1 && !doc_ends && span > 1;       // my columns end inside a longer document
-          if (mine_ends) {
-            // One partial slot per warp (shared memory is full: 227 KB of tiles).  The previous tile's partial is read by its
-            // finisher before that warp hands the previous accumulator back, so "every epilogue warp has drained the previous
-            // tile" (the accumulator's empty barrier) is what makes the slot free.
-            if (it > 0) mbar_wait(&tempty_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-            part[(quad * (SC_EPQ - 1) + slot) * 32 + lane] = m;                           // handed to the warp that finishes the document
-          } else if (doc_ends) {
-            if (span > 1) {
-              asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");   // the partners' partial maxima are in smem
-              for (int s2 = slot - span + 1; s2 < slot; ++s2) m = fmaxf(m, part[(quad * (SC_EPQ - 1) + s2) * 32 + lane]);
-            }
-            float sum = (lane < p.Lq) ? m : 0.f;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const int64_t doc = doc0 + din;
-            if (lane == 0 && q < p.nq && doc < p.Nd) p.out[size_t(q) * p.ld_out + doc] = sum;
-            m = SC_PAD_FILL;
-          }
-        }
-        // a warp that only handed a partial over still meets the quadrant's barrier (once per tile, every warp)
-        if (span > 1 && (slot % span) != span - 1) asm volatile("bar.sync %0, %1;" ::"r"(quad_bar), "r"(32 * SC_EPQ) : "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    // one specialised loop per (document length, masked or not): the tile's column -> (document, token) map, the chunks that end
+    // a document and the hand-over between warps are compile-time facts of each instance, not per-tile branches
+    if (p.doclen) {
+      switch (p.Ld) {
+        case 32: scan_epilogue<32, true>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        case 64: scan_epilogue<64, true>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        case 128: scan_epilogue<128, true>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        default: scan_epilogue<256, true>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+      }
+    } else {
+      switch (p.Ld) {
+        case 32: scan_epilogue<32, false>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        case 64: scan_epilogue<64, false>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        case 128: scan_epilogue<128, false>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
+        default: scan_epilogue<256, false>(p, tmem_base, tfull_bar, tempty_bar, part, quad, slot, lane); break;
       }
     }
   }
