@@ -660,10 +660,14 @@ class MaxsimScanWorkload:
         self.Nd, self.Ld, self.Lq = args.n_docs or 1_000_000, 128, 32
         self.nq, self.k = args.nq or 64, args.k
         self.rank, self.world, self.device = rank, world, device
+        self.ragged = bool(getattr(args, "ragged_doclen", False))
+        self.doclen = None
 
     def config(self):
         return {"workload": f"configs[2] token store, full scan: {self.Nd} docs x {self.Ld} x 128 bf16, batch of {self.nq} queries x {self.Lq} tokens "
-                            f"against every document -> top-{self.k}", "l2": f"token store {self.Nd * self.Ld * 256 / 1e9:.1f} GB >> L2",
+                            f"against every document -> top-{self.k}" + (", document lengths ~U{32..128} (masked epilogue; FLOPs counted on the "
+                                                                        "padded store, which is what the tensor cores multiply)" if self.ragged else ""),
+                "l2": f"token store {self.Nd * self.Ld * 256 / 1e9:.1f} GB >> L2",
                 "parallelism": f"doc-sharded x{self.world}" if self.world > 1 else "single GPU"}
 
     def setup(self):
@@ -673,14 +677,17 @@ class MaxsimScanWorkload:
         self.D = synth.unit_tokens_bf16(self.Nd, self.Ld, 128, 5 + self.rank, self.device)
         self.Q = synth.unit_tokens_bf16(self.nq, self.Lq, 128, 7, self.device)
         self.Q_host = self.Q.cpu().pin_memory()
+        if self.ragged:                          # SURVEY 8d C3's masking variant: doclen ~U{32..128}, seed 6
+            g = torch.Generator(device=self.device).manual_seed(6 + self.rank)
+            self.doclen = torch.randint(32, self.Ld + 1, (self.Nd,), generator=g, device=self.device, dtype=torch.int32)
 
     def step(self):
-        s, i = self.engine.maxsim_scan_topk(self.D, None, self.Q, self.k, id_base=self.rank * self.Nd)
+        s, i = self.engine.maxsim_scan_topk(self.D, self.doclen, self.Q, self.k, id_base=self.rank * self.Nd)
         return self.engine.allgather_merge(s, i, self.k)
 
     def e2e_step(self):
         q = self.Q_host.to(self.device, non_blocking=True)
-        s, i = self.engine.maxsim_scan_topk(self.D, None, q, self.k, id_base=self.rank * self.Nd)
+        s, i = self.engine.maxsim_scan_topk(self.D, self.doclen, q, self.k, id_base=self.rank * self.Nd)
         s, i = self.engine.allgather_merge(s, i, self.k)
         return s.cpu(), i.cpu()
 
@@ -1139,6 +1146,7 @@ def main():
     ap.add_argument("--kc", type=int, default=0, help="hybrid: per-channel list length (default k); 500 gives the 1000-candidate rerank of SURVEY 8d C5")
     ap.add_argument("--colbert-mode", default="rerank", choices=["rerank", "scan"],
                     help="hybrid: MaxSim over the fused candidate union, or ColBERT as a first-stage channel over the whole token store")
+    ap.add_argument("--ragged-doclen", action="store_true", help="maxsim_scan: document lengths ~U{32..128} instead of full-length documents")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-sms", default="auto", help="hybrid workload: SMs of the dense scan when it runs side by side with the BM25 "
                     "scan (the rest go to BM25); 0 = one after the other; auto = time a few splits and keep the fastest")

@@ -66,6 +66,28 @@ __device__ __forceinline__ float scan_max32(const uint32_t (&vv)[32], float m) {
   return fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
 }
 
+// The same for a chunk whose document ends inside it: only the first `rem` (1 .. 31, warp-uniform) words count.  Whole groups of
+// eight go through max trees; the one group that holds the document's end selects its words against the pad value first --
+// independent selects and a tree, not a 32-deep chain of predicated maxima through m.
+__device__ __forceinline__ float scan_max32_masked(const uint32_t (&vv)[32], float m, int rem) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (rem > 8 * g) {
+      float x[8];
+      if (rem >= 8 * g + 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(vv[8 * g + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (8 * g + j < rem) ? __uint_as_float(vv[8 * g + j]) : SC_PAD_FILL;
+      }
+      const float a = fmaxf(fmaxf(x[0], x[1]), x[2]), b = fmaxf(fmaxf(x[3], x[4]), x[5]), c = fmaxf(fmaxf(x[6], x[7]), m);
+      m = fmaxf(fmaxf(a, b), c);
+    }
+  }
+  return m;
+}
+
 // Epilogue of one warp: SC_EPQ warps per TMEM lane quadrant (= query inside the block); warp `slot` of a quadrant takes columns
 // [slot * SC_WCOLS, (slot + 1) * SC_WCOLS) of every tile.  A document longer than that (LD = 256) spans two warps: their partial
 // maxima meet in shared memory and the warp that holds the document's last columns finishes it.  LD (32, 64, 128 or 256) and
@@ -102,15 +124,22 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams& p, uint32_t tmem
     const int64_t dt1 = min(p.DT, dt0 + p.chunk_tiles);
     const int q = qb * 4 + quad;
     float* out_row = p.out + size_t(q < p.nq ? q : 0) * p.ld_out;
+    // document lengths of a tile (lane d holds document d's), fetched one tile ahead: when the epilogue is what paces the
+    // kernel nothing hides a load issued at the top of the tile it is needed in
+    auto load_dl = [&](int64_t t) {
+      int dl = 0;
+      if (HAS_DL && lane < DPT && t < dt1) {
+        const int64_t doc = t * DPT + lane;
+        dl = doc < p.Nd ? min(__ldg(p.doclen + doc), LD) : 0;
+      }
+      return dl;
+    };
+    int dl_next = load_dl(dt0);
     for (int64_t dt = dt0; dt < dt1; ++dt, ++it) {
       const int64_t doc0 = dt * DPT;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      // document lengths of the tile, fetched before the accumulator is waited for
-      int dl_mine = 0;
-      if (HAS_DL && lane < DPT) {
-        const int64_t doc = doc0 + lane;
-        dl_mine = doc < p.Nd ? min(p.doclen[doc], LD) : 0;
-      }
+      const int dl_mine = dl_next;
+      dl_next = load_dl(dt + 1);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * SC_BN;
@@ -125,25 +154,20 @@ __device__ __forceinline__ void scan_epilogue(const ScanParams& p, uint32_t tmem
 #pragma unroll
       for (int i = 0; i < SC_WCHUNKS; ++i)
         dl_c[i] = HAS_DL ? __shfl_sync(0xffffffffu, dl_mine, din_of(i)) : LD;
-      if (off_of(0) < dl_c[0]) tmem_ld_32x32(taddr + c0 * 32, v[0]);
+      tmem_ld_32x32(taddr + c0 * 32, v[0]);      // every chunk is read, masked or not: TMEM bandwidth is plentiful, branches around an aligned load are not free
 #pragma unroll
       for (int i = 0; i < SC_WCHUNKS; ++i) {
         const int c = c0 + i;
         const int off = off_of(i), dl = dl_c[i];
         const bool live = off < dl;                                             // warp-uniform: the chunk holds unmasked tokens
         tmem_ld_wait();
-        if (i + 1 < SC_WCHUNKS) {
-          const int j = i + 1 < SC_WCHUNKS ? i + 1 : i;
-          if (off_of(j) < dl_c[j]) tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
-        }
+        if (i + 1 < SC_WCHUNKS) tmem_ld_32x32(taddr + (c + 1) * 32, v[(i + 1) & 1]);
         if (live) {
           const uint32_t (&vv)[32] = v[i & 1];
           if (!HAS_DL || off + 32 <= dl) {
             m = scan_max32(vv, m);
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (off + j < dl) m = fmaxf(m, __uint_as_float(vv[j]));
+            m = scan_max32_masked(vv, m, dl - off);
           }
         }
         const bool doc_ends = off + 32 == LD;                                     // the document's last columns are in this chunk
