@@ -587,10 +587,12 @@ class HybridShard:
     def search_device(self, Qd: torch.Tensor, q_indptr: torch.Tensor, q_term: torch.Tensor, max_query_terms: int,
                       Qtok: Optional[torch.Tensor], k: int = 100, kc: int = 100, method: str = "weighted_sum",
                       w_dense: float = 0.6, w_bm25: float = 0.4, w_colbert: float = 0.35, colbert_mode: str = "rerank",
-                      **fuse_kw):
+                      qtok_ready: Optional[torch.cuda.Event] = None, **fuse_kw):
         """colbert_mode "rerank": MaxSim over the fused candidate union (the north star's rerank).  "scan": ColBERT as a
         first-stage channel over the whole corpus like the reference (hybrid_retriever.py:299) -- every document of the
-        shard is scored by the batched full-corpus kernel; needs one token row per document (no id aliasing)."""
+        shard is scored by the batched full-corpus kernel; needs one token row per document (no id aliasing).
+        qtok_ready: an event after which Qtok holds its data (search() uploads the query token matrix, five sixths of a
+        step's input bytes, on a copy stream while the scans run); waited for right before the MaxSim stage."""
         import torch.distributed as dist
         # local scans first, one exchange for all channels afterwards
         if self.dense_sms > 0:
@@ -600,6 +602,8 @@ class HybridShard:
         kw = dict(method=method, w_dense=w_dense, w_bm25=w_bm25, w_colbert=w_colbert, **fuse_kw)
         scan = colbert_mode == "scan" and self.tokens is not None and Qtok is not None
         if scan:
+            if qtok_ready is not None:
+                torch.cuda.current_stream(self.X.device).wait_event(qtok_ready)
             if self.tokens.shape[0] != self.X.shape[0] or self.tok_row_base != self.id_base:
                 raise LragError("colbert_mode='scan' needs one token row per document of the shard")
             cs, ci = maxsim_scan_topk(self.tokens, self.doclen, Qtok, min(kc, int(self.tokens.shape[0])), id_base=self.id_base)
@@ -617,6 +621,8 @@ class HybridShard:
         _, cand_gid = fuse_topk((ds, di), (bs, bi), None, k=2 * kc, method=method, w_dense=w_dense, w_bm25=w_bm25)
         rows = torch.where(cand_gid >= 0, cand_gid % max(1, self.tok_rows_total), cand_gid) - self.tok_row_base
         owned = (cand_gid >= 0) & (rows >= 0) & (rows < self.tokens.shape[0])
+        if qtok_ready is not None:
+            torch.cuda.current_stream(self.X.device).wait_event(qtok_ready)
         cs = maxsim_scores(self.tokens, self.doclen, Qtok, torch.where(owned, rows, torch.full_like(rows, -1)))
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(cs, op=dist.ReduceOp.MAX, group=self.group)      # every candidate has exactly one owner
@@ -628,7 +634,20 @@ class HybridShard:
         """Host (pinned) inputs -> H2D -> search_device -> D2H; returns CPU (scores [nq, k], ids [nq, k])."""
         dev = self.X.device
         up = lambda t: None if t is None else t.to(dev, non_blocking=True)
-        s, i = self.search_device(up(Qd_host), up(qi_host), up(qt_host), max_query_terms, up(Qtok_host), k=k, **kw)
+        Qtok, ready = None, None
+        if Qtok_host is not None:
+            # The query token matrix is needed only by the MaxSim stage: it travels on a copy stream while the scans run.  The
+            # buffer belongs to the calling stream (allocated, last used and freed there); the copy stream joins the calling
+            # stream's position first, so whatever last used that memory is done before the copy lands in it.
+            main = torch.cuda.current_stream(dev)
+            side = self._copy_stream = getattr(self, "_copy_stream", None) or torch.cuda.Stream(dev)
+            Qtok = torch.empty(Qtok_host.shape, dtype=Qtok_host.dtype, device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                Qtok.copy_(Qtok_host, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(side)
+        s, i = self.search_device(up(Qd_host), up(qi_host), up(qt_host), max_query_terms, Qtok, k=k, qtok_ready=ready, **kw)
         return s.cpu(), i.cpu()
 
 

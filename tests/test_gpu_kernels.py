@@ -569,6 +569,17 @@ def test_hybrid_shard_matches_oracle_pipeline(eng):
             m = min(len(ref), k + 8)
             check_topk_parity(s[q:q + 1], i[q:q + 1], np.array([[r["score"] for r in ref[:m]]]), np.array([[r["id"] for r in ref[:m]]]),
                               k, 2e-3, what=f"hybrid-{method}")
+    # the host-buffer entry (pinned inputs; the query token matrix travels on a copy stream while the scans run) returns what
+    # search_device returns, call after call (the upload buffer is recycled by the allocator between calls)
+    host_in = [t.cpu().pin_memory() for t in (Qd, torch.from_numpy(qi), torch.from_numpy(qt), Qtd)]
+    for mode in ("rerank", "scan"):
+        want_s, want_i = shard.search_device(Qd, torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), mx, Qtd, k=k, kc=kc,
+                                             colbert_mode=mode)
+        for _ in range(4):
+            junk = torch.randn(nq * Lq * 128, device="cuda")        # something else takes and returns memory in between
+            del junk
+            got_s, got_i = shard.search(host_in[0], host_in[1], host_in[2], mx, host_in[3], k=k, kc=kc, colbert_mode=mode)
+            assert torch.equal(got_s, want_s.cpu()) and torch.equal(got_i, want_i.cpu())
     # ColBERT as a first-stage channel over the whole corpus (the reference's own arrangement, hybrid_retriever.py:299)
     s, i = shard.search_device(Qd, torch.from_numpy(qi).cuda(), torch.from_numpy(qt).cuda(), mx, Qtd, k=k, kc=kc, method="rrf_norm_blend",
                                colbert_mode="scan")
