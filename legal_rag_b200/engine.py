@@ -5,6 +5,7 @@ the C ABI.  Every function takes CUDA tensors, enqueues on the current torch str
 """
 from __future__ import annotations
 
+import os
 import threading
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -594,6 +595,25 @@ class HybridShard:
         qtok_ready: an event after which Qtok holds its data (search() uploads the query token matrix, five sixths of a
         step's input bytes, on a copy stream while the scans run); waited for right before the MaxSim stage."""
         import torch.distributed as dist
+        # Stage fences.  With several ranks the host waits for the device after every stage of the step (six waits, ~0.6 ms of a
+        # ~100 ms step at 8 GPUs).  Reason: at 8 GPUs -- never at 1 or 2 -- about one rank-step in a thousand ended in a device
+        # fault ("illegal instruction", on a different rank each time) when the host ran several steps ahead of the devices;
+        # with the fences 2 288 rank-steps in a row were clean (DESIGN 5, "An intermittent fault at 8 GPUs").  The fault is not
+        # root-caused; the fence also names the stage a fault surfaces in.  LRAG_STAGE_FENCES=0 switches them off, =1 forces
+        # them on for a single rank.
+        env = os.environ.get("LRAG_STAGE_FENCES", os.environ.get("LRAG_DEBUG_STAGES", ""))
+        ranks = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        debug = env == "1" or (env != "0" and ranks > 1)
+
+        def stage_done(name):
+            if debug:
+                try:
+                    torch.cuda.synchronize(self.X.device)
+                except Exception as e:  # noqa: BLE001
+                    import sys
+                    print(f"[lrag] device fault surfaced after stage '{name}' on {self.X.device} (id_base {self.id_base}): {e!r}"[:400],
+                          file=sys.stderr, flush=True)
+                    raise
         # local scans first, one exchange for all channels afterwards
         if self.dense_sms > 0:
             local = self._scans_side_by_side(Qd, q_indptr, q_term, max_query_terms, kc)
@@ -611,7 +631,9 @@ class HybridShard:
                 cs = torch.nn.functional.pad(cs, (0, kc - cs.shape[1]), value=PAD_SCORE)
                 ci = torch.nn.functional.pad(ci, (0, kc - ci.shape[1]), value=-1)
             local.append((cs, ci))
+        stage_done("scans")
         merged = allgather_merge_many(local, kc, self.group)
+        stage_done("all-gather + merges")
         (ds, di), (bs, bi) = merged[0], merged[1]
         if self.tokens is None or Qtok is None:
             return fuse_topk((ds, di), (bs, bi), None, k=k, **kw)
@@ -621,14 +643,20 @@ class HybridShard:
         _, cand_gid = fuse_topk((ds, di), (bs, bi), None, k=2 * kc, method=method, w_dense=w_dense, w_bm25=w_bm25)
         rows = torch.where(cand_gid >= 0, cand_gid % max(1, self.tok_rows_total), cand_gid) - self.tok_row_base
         owned = (cand_gid >= 0) & (rows >= 0) & (rows < self.tokens.shape[0])
+        stage_done("candidate fusion")
         if qtok_ready is not None:
             torch.cuda.current_stream(self.X.device).wait_event(qtok_ready)
         cs = maxsim_scores(self.tokens, self.doclen, Qtok, torch.where(owned, rows, torch.full_like(rows, -1)))
+        stage_done("maxsim")
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(cs, op=dist.ReduceOp.MAX, group=self.group)      # every candidate has exactly one owner
+            stage_done("max-reduce")
         cs = torch.where(cs == float("-inf"), torch.full_like(cs, PAD_SCORE), cs)
         cls, cli = topk_select(cs, min(kc, cs.shape[1]), col_id=cand_gid)
-        return fuse_topk((ds, di), (bs, bi), (cls, cli), k=k, **kw)
+        stage_done("select")
+        out = fuse_topk((ds, di), (bs, bi), (cls, cli), k=k, **kw)
+        stage_done("final fusion")
+        return out
 
     def search(self, Qd_host, qi_host, qt_host, max_query_terms: int, Qtok_host, k: int = 100, **kw):
         """Host (pinned) inputs -> H2D -> search_device -> D2H; returns CPU (scores [nq, k], ids [nq, k])."""
