@@ -603,10 +603,10 @@ class HybridShard:
         # them on for a single rank.
         env = os.environ.get("LRAG_STAGE_FENCES", os.environ.get("LRAG_DEBUG_STAGES", ""))
         ranks = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
-        debug = env == "1" or (env != "0" and ranks > 1)
+        fenced = env == "1" or (env != "0" and ranks > 1)
 
         def stage_done(name):
-            if debug:
+            if fenced:
                 try:
                     torch.cuda.synchronize(self.X.device)
                 except Exception as e:  # noqa: BLE001
