@@ -17,6 +17,27 @@ from ..schemas import LawChunk, chunk_from_obj
 from . import artifacts, encoders
 
 
+def compact_known_terms(q_indptr: np.ndarray, q_term: np.ndarray, cap: int):
+    """Drops the out-of-vocabulary tokens (-1) of every query, then keeps at most `cap` tokens per query (the first ones).
+    Tokens outside the vocabulary score nothing in rank_bm25 (`self.doc_freqs[...].get(q) or 0`, bm25_retriever.py:74), so
+    they must not take up slots of the kernel's per-query term table -- jieba emits whitespace and punctuation as tokens
+    of their own.  -> (q_indptr int64 [nq + 1], q_term int32, longest kept query, longest query before the cap)."""
+    q_indptr = np.asarray(q_indptr, dtype=np.int64)
+    q_term = np.asarray(q_term, dtype=np.int32)
+    known = q_term >= 0
+    seen = np.concatenate([[0], np.cumsum(known)]).astype(np.int64)
+    lens = seen[q_indptr[1:]] - seen[q_indptr[:-1]]
+    q_term = q_term[known]
+    q_indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    longest = int(lens.max()) if lens.size else 0
+    if longest > cap:
+        keep = np.concatenate([np.arange(a, min(b, a + cap)) for a, b in zip(q_indptr[:-1], q_indptr[1:])]).astype(np.int64)
+        q_term = q_term[keep]
+        lens = np.minimum(lens, cap)
+        q_indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    return q_indptr, q_term, min(longest, cap), longest
+
+
 class BM25Retriever:
     def __init__(self, cfg, tokenizer: Optional[Callable[[str], List[str]]] = None):
         self.cfg = cfg
@@ -63,25 +84,12 @@ class BM25Retriever:
         host, dev = self.host_index, self.device_index
         k = max(1, min(int(top_k), engine.LRAG_MAX_K))
         qi, qt, _ = host.encode_queries([list(t) for t in token_lists])
-        # tokens outside the vocabulary score nothing (rank_bm25: `self.doc_freqs[...].get(q) or 0`), so they do not take up
-        # slots of the kernel's per-query term table (jieba emits whitespace and punctuation as tokens of their own)
-        known = qt >= 0
-        seen = np.concatenate([[0], np.cumsum(known)]).astype(np.int64)
-        lens = seen[qi[1:]] - seen[qi[:-1]]
-        qt = qt[known]
-        qi = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        mx = int(lens.max()) if lens.size else 0
-        if mx > engine.LRAG_BM25_MAX_QUERY_TERMS:
+        qi, qt, mx, longest = compact_known_terms(qi, qt, engine.LRAG_BM25_MAX_QUERY_TERMS)
+        if longest > engine.LRAG_BM25_MAX_QUERY_TERMS:
             # rank_bm25 scores every token (bm25_retriever.py:74); the kernel's per-query term table holds 128
             logging.getLogger("legal_rag_b200.retrieval").warning(
                 "[BM25] a query of %d in-vocabulary tokens is scored on its first %d (kernel limit LRAG_BM25_MAX_QUERY_TERMS); "
-                "the reference would score all of them", mx, engine.LRAG_BM25_MAX_QUERY_TERMS)
-            cap = engine.LRAG_BM25_MAX_QUERY_TERMS
-            keep = np.concatenate([np.arange(a, min(b, a + cap)) for a, b in zip(qi[:-1], qi[1:])]).astype(np.int64)
-            qt = qt[keep]
-            lens = np.minimum(lens, cap)
-            qi = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-            mx = cap
+                "the reference would score all of them", longest, engine.LRAG_BM25_MAX_QUERY_TERMS)
         return engine.bm25_topk(dev, torch.from_numpy(qi).to(self.device), torch.from_numpy(qt).to(self.device), mx, k)
 
     def search(self, query: str, top_k: int) -> List[Tuple[LawChunk, float]]:

@@ -471,3 +471,29 @@ def test_transformers_colbert_encoder_restates_the_checkpoint_pipeline(tmp_path)
     # not a directory, nothing registered: the channel cannot be built, and says why
     with pytest.raises(RuntimeError, match="not a local checkpoint directory"):
         encoders.make_token_encoder("colbert-ir/colbertv2.0", "cpu")
+
+
+def test_bm25_query_compaction_drops_unknown_tokens_before_the_term_limit():
+    """BM25Retriever.search_ids: out-of-vocabulary tokens (-1) leave the query before the kernel's 128-slot term table is
+    filled; what is left is cut to the first `cap` tokens.  Checked against a per-query loop, with empty and all-unknown
+    queries, on random ragged batches."""
+    from legal_rag_b200.retrieval.bm25_retriever import compact_known_terms
+    rng = np.random.default_rng(3)
+    for trial in range(50):
+        nq = int(rng.integers(0, 9))
+        lists = []
+        for _ in range(nq):
+            n = int(rng.integers(0, 40)) if rng.random() < 0.8 else int(rng.integers(100, 400))
+            t = rng.integers(0, 1000, n).astype(np.int32)
+            t[rng.random(n) < (1.0 if rng.random() < 0.1 else 0.4)] = -1
+            lists.append(t)
+        qi = np.concatenate([[0], np.cumsum([len(t) for t in lists])]).astype(np.int64)
+        qt = np.concatenate(lists).astype(np.int32) if lists else np.zeros(0, np.int32)
+        cap = int(rng.choice([4, 16, 128]))
+        gi, gt, mx, longest = compact_known_terms(qi, qt, cap)
+        want = [t[t >= 0] for t in lists]
+        assert longest == max((len(w) for w in want), default=0)
+        want = [w[:cap] for w in want]
+        assert mx == max((len(w) for w in want), default=0)
+        assert gi.dtype == np.int64 and gt.dtype == np.int32 and gi.tolist() == np.concatenate([[0], np.cumsum([len(w) for w in want])]).tolist()
+        assert gt.tolist() == (np.concatenate(want).tolist() if want else [])
